@@ -1,0 +1,168 @@
+/*
+ * vo_b200.h -- C-ABI of the B200-native visual-odometry front-end (libvo_b200.so).
+ *
+ * This is the drop-in boundary for the per-frame hot path of ZhenghaoFei/visual_odom:
+ * every entry point replaces one OpenCV-backed function of the reference's libfeature /
+ * libvisualOdometry shared libraries (reference src/CMakeLists.txt:16-19,31-34).  The C++
+ * facade in include/compat/ keeps the reference's own signatures (feature.h, visualOdometry.h)
+ * and forwards to these functions; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, no torch / OpenCV types; caller owns every buffer; outputs are capacity-passed.
+ *   - images are 8-bit single channel (CV_8UC1), row pitch in bytes (reference utils.cpp:179,189).
+ *   - points are {float x, y} (cv::Point2f), status is unsigned char, ages are int32.
+ *   - every call is synchronous at return unless it says "async" (then it is ordered on the
+ *     context's stream; see vo_set_stream / vo_sync).
+ *   - return value: VO_OK (0) or a negative VO_E_* code; vo_last_error() gives the text.
+ *   - there is NO CPU fallback: if no sm_100-class GPU is usable, vo_create fails.
+ *   - a context is not thread-safe; distinct contexts are independent (one per host thread/GPU).
+ */
+#ifndef VO_B200_H
+#define VO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VO_API __attribute__((visibility("default")))
+#else
+#define VO_API
+#endif
+
+#define VO_OK 0
+#define VO_E_INVALID (-1)        /* bad argument                                             */
+#define VO_E_CUDA (-2)           /* CUDA runtime/driver failure (text in vo_last_error)      */
+#define VO_E_TOO_FEW_POINTS (-3) /* PnP with < 4 points (the reference aborts in cv::solvePnPRansac) */
+#define VO_E_UNSUPPORTED (-4)    /* parameter outside what the kernels are built for         */
+#define VO_E_CAPACITY (-5)       /* caller buffer / context capacity too small               */
+
+typedef struct vo_ctx vo_ctx;
+
+typedef struct vo_point2f { float x, y; } vo_point2f;
+typedef struct vo_point3f { float x, y, z; } vo_point3f;
+
+/* All literals the reference hard-codes, as run-time parameters ("Config"). */
+typedef struct vo_params {
+    int fast_threshold;      /* 20      reference src/feature.cpp:43                          */
+    int fast_nonmax;         /* 1       reference src/feature.cpp:44                          */
+    int lk_win;              /* 21      reference src/feature.cpp:127 (only 21 is built)      */
+    int lk_max_level;        /* 3       reference src/feature.cpp:136 (0-based: 4 images)     */
+    int lk_max_iters;        /* 30      reference src/feature.cpp:128                         */
+    double lk_epsilon;       /* 0.01    reference src/feature.cpp:128                         */
+    double lk_min_eig;       /* 0.001   reference src/feature.cpp:136                         */
+    int circ_threshold;      /* 0       reference src/visualOdometry.cpp:120                  */
+    int pnp_iterations;      /* 500     reference src/visualOdometry.cpp:168                  */
+    float pnp_reproj_error;  /* 0.5     reference src/visualOdometry.cpp:169                  */
+    double pnp_confidence;   /* 0.999   reference src/visualOdometry.cpp:170                  */
+    int max_features;        /* per-unit feature capacity of the context (default 8192)       */
+    int max_units;           /* work units the batched path can hold at once (default 1)      */
+} vo_params;
+
+VO_API void vo_default_params(vo_params* p);
+
+/* Create a context on CUDA device `device`.  Fails (VO_E_CUDA) when no GPU is present. */
+VO_API int vo_create(int device, const vo_params* params, vo_ctx** out);
+VO_API void vo_destroy(vo_ctx* ctx);
+VO_API const char* vo_last_error(const vo_ctx* ctx);
+/* Run all subsequent work on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
+VO_API int vo_set_stream(vo_ctx* ctx, void* cuda_stream);
+VO_API int vo_sync(vo_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's "gpu_launches"). */
+VO_API long long vo_kernel_launches(const vo_ctx* ctx);
+/* Accumulated device time (ms) of the LK ring kernel launches since the last reset,
+ * measured with CUDA events on the launching stream; n = launches counted. */
+VO_API int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset);
+
+/* ---- A1: cv::FAST(image, kps, threshold, nonmax) + KeyPoint::convert ------------------------
+ * replaces featureDetectionFast(), reference src/feature.cpp:39-47 (decl feature.h:48).
+ * Output in raster order (y, then x), integer coordinates as float.  *n_out is the number of
+ * corners found; at most `cap` are written (VO_E_CAPACITY if n_out > cap, buffer still filled). */
+VO_API int vo_fast_detect(vo_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch,
+                          vo_point2f* out, float* response /* optional */, int cap, int* n_out);
+
+/* ---- one cv::calcOpticalFlowPyrLK call ---------------------------------------------------------
+ * replaces the call inside featureTracking(), reference src/feature.cpp:72 (decl feature.h:52),
+ * and is the unit the ring below chains.  err may be NULL. */
+VO_API int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch,
+                       const vo_point2f* prev_pts, int n, vo_point2f* next_pts, uint8_t* status, float* err);
+
+/* ---- A2 + A3: circularMatching() ---------------------------------------------------------------
+ * replaces circularMatching(), reference src/feature.cpp:118-148 (decl feature.h:61-65), i.e. the
+ * four chained LK calls L0->R0->R1->L1->L0 and deleteUnmatchFeaturesCircle() (src/feature.cpp:76-116).
+ *   pts_l0[n]            input features (points_l_0)
+ *   ages_io[n]           in: current_features.ages; out: ages+1, compacted to *n_kept (may be NULL)
+ *   o_l0,o_r0,o_l1,o_r1,o_l0_ret  capacity n each: the five point vectors after the erase loop
+ *   status4              optional, 4*n bytes: raw status of the four calls, original indexing
+ *   raw4                 optional, 4*n points: raw outputs of the four calls (R0,R1,L1,L0_ret), original indexing
+ *   kept_idx[n]          original indices of the survivors, ascending; *n_kept their count */
+VO_API int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* r0, const uint8_t* l1,
+                             const uint8_t* r1, int w, int h, size_t pitch, const vo_point2f* pts_l0, int n,
+                             int32_t* ages_io, vo_point2f* o_l0, vo_point2f* o_r0, vo_point2f* o_l1,
+                             vo_point2f* o_r1, vo_point2f* o_l0_ret, uint8_t* status4, vo_point2f* raw4,
+                             int32_t* kept_idx, int* n_kept);
+
+/* ---- A8: cv::triangulatePoints + cv::convertPointsFromHomogeneous ------------------------------
+ * replaces the call site reference src/main.cpp:170-171 (and Frame::triangulateFeaturePoints,
+ * src/Frame.cpp:25-28).  P_l, P_r: row-major 3x4 float (CV_32F, main.cpp:73-74). */
+VO_API int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[12], const vo_point2f* pts_l,
+                          const vo_point2f* pts_r, int n, vo_point3f* X);
+
+/* ---- A9: cv::solvePnPRansac(..., SOLVEPNP_ITERATIVE, useExtrinsicGuess) + cv::Rodrigues --------
+ * replaces the pose solve of trackingFrame2Frame(), reference src/visualOdometry.cpp:161-189.
+ *   K            row-major 3x3 float intrinsics (built from P_l, visualOdometry.cpp:163-165)
+ *   rvec_io      in: initial rvec (the reference resets it to 0 every call, :162); out: solution
+ *   tvec_io      in: extrinsic guess (previous translation, main.cpp:82,181); out: solution
+ *   inliers[n]   ascending inlier indices (CV_32S column in the reference), *n_inliers their count
+ *   R_out        row-major 3x3 double = Rodrigues(rvec)
+ * Returns VO_E_TOO_FEW_POINTS for n < 4 (the reference would abort with cv::Exception). */
+VO_API int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f* x, int n, const float K[9],
+                         double rvec_io[3], double tvec_io[3], int32_t* inliers, int* n_inliers,
+                         double R_out[9], int* ransac_iters /* optional */);
+
+/* ---- batched whole-path API (configs 4/5 of BASELINE.json, bench.py, multi-GPU sharding) ------
+ * One work unit = one stereo pair-of-pairs + its feature list (SURVEY.md section 8d "Work unit").
+ * The batched path keeps everything device-resident between stages:
+ *   FAST on l0 (when pts == NULL) -> even-stride selection of select_n corners
+ *   -> pyramids -> LK ring -> status/negative/circular filters -> triangulation -> PnP/RANSAC. */
+typedef struct vo_unit {
+    const uint8_t *l0, *r0, *l1, *r1;   /* HOST images (w x h, pitch) unless VO_UNIT_DEVICE_IMAGES   */
+    const vo_point2f* pts;              /* HOST features of l0, or NULL = detect on the GPU         */
+    int n_pts;                          /* features in pts; with pts==NULL: number to select        */
+    double t_prev[3];                   /* extrinsic guess for the pose solve                       */
+} vo_unit;
+
+typedef struct vo_unit_result {
+    int n_features;      /* features fed to the ring                                   */
+    int n_detected;      /* FAST corners found on l0 (0 when pts were given)           */
+    int n_tracked;       /* survivors of deleteUnmatchFeaturesCircle (A3)              */
+    int n_valid;         /* survivors of checkValidMatch/removeInvalidPoints (A5/A6)   */
+    int n_inliers;       /* RANSAC inliers                                             */
+    int ransac_iters;    /* iterations the adaptive loop ran                           */
+    int pnp_status;      /* VO_OK or VO_E_TOO_FEW_POINTS                               */
+    double rvec[3], tvec[3], R[9];
+} vo_unit_result;
+
+/* Allocate/resize the device-resident batch state for n_units units of w x h images. */
+VO_API int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const float P_l[12], const float P_r[12]);
+/* async: copy the units' images (and features) host->device on the context's stream. */
+VO_API int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch);
+/* async: run the whole path for the uploaded units. */
+VO_API int vo_batch_run(vo_ctx* ctx);
+/* async D2H of the per-unit result records into pinned staging + sync + copy to `results`. */
+VO_API int vo_batch_download(vo_ctx* ctx, vo_unit_result* results, int n_units);
+/* upload + run + download in one call: the end-to-end entry point. */
+VO_API int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch, vo_unit_result* results);
+/* Fetch the per-unit arrays of the last run (any pointer may be NULL). Capacity = max_features.
+ *   pts4: 4 x n_valid points (L0,R0,L1,R1 after A6);  kept_idx: n_valid original indices;
+ *   X: n_valid 3-D points;  inliers: n_inliers indices into the n_valid list. */
+VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,
+                          vo_point3f* X, int32_t* inliers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VO_B200_H */

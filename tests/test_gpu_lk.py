@@ -1,0 +1,65 @@
+"""GPU parity: K1 pyramid + K2 LK ring + K3 filters vs the oracle (bit-exact).
+
+The oracle (oracle/lk_ref.c) is pinned bit-for-bit against cv2 4.13.0 in test_oracle_lk.py, so
+bit-equality here is bit-equality with the reference's cv::calcOpticalFlowPyrLK.
+"""
+import numpy as np
+import pytest
+
+from visual_odom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _border_points(w, h):
+    return np.array([[0, 0], [-5, 3], [w - 1, h - 1], [w + 5, 10], [3, h + 30], [-30, -30], [w - 0.5, 5.5],
+                     [10.25, -21.5], [w + 20.9, h / 2], [5, -10.99], [-11.01, 7]], np.float32)
+
+
+@pytest.mark.parametrize("w,h,seed,scene", [(1241, 376, 0, "v1"), (1241, 376, 1, "v0"), (640, 480, 2, "v1"), (333, 129, 3, "v0")])
+def test_single_call_bit_exact(ctx, w, h, seed, scene):
+    from oracle import cref
+    u = synth.stereo_unit(w, h, seed, scene=scene)
+    corners, _ = cref.fast_detect(u["l0"])
+    pts = synth.select_features(corners, 1500)
+    rng = np.random.default_rng(seed)
+    pts = np.concatenate([pts + rng.uniform(-0.5, 0.5, pts.shape).astype(np.float32), _border_points(w, h)])
+    for a, b in ((u["l0"], u["r0"]), (u["l0"], u["l1"])):
+        ro, rs, re = cref.lk_track(a, b, pts)
+        go, gs, ge = ctx.lk_track(a, b, pts)
+        assert np.array_equal(gs, rs), f"status differs at {np.nonzero(gs != rs)[0][:10]}"
+        assert np.array_equal(go, ro), f"positions differ: max {np.abs(go - ro).max()} at {np.nonzero((go != ro).any(1))[0][:10]}"
+        ok = rs == 1
+        assert np.array_equal(ge[ok], re[ok])
+        assert ok.sum() > 0.8 * len(pts)
+
+
+def test_ring_and_filters_bit_exact(ctx):
+    from oracle import cref, ref_path
+    w, h = 1241, 376
+    u = synth.stereo_unit(w, h, 5)
+    corners, _ = cref.fast_detect(u["l0"])
+    pts = np.concatenate([synth.select_features(corners, 2000), _border_points(w, h)])
+    fs = ref_path.FeatureSet()
+    fs.points = pts.copy(); fs.ages = np.arange(len(pts), dtype=np.int32) % 7
+    ages0 = fs.ages.copy()
+    ref = ref_path.circular_matching(u["l0"], u["r0"], u["l1"], u["r1"], pts, fs, backend="c")
+    got = ctx.circular_match(u["l0"], u["r0"], u["l1"], u["r1"], pts, ages=ages0)
+    assert np.array_equal(got["status4"], ref["raw"]["status"])
+    for k, name in enumerate(("r0", "r1", "l1", "l0_ret")):
+        assert np.array_equal(got["raw4"][k], ref["raw"][name]), name
+    assert np.array_equal(got["kept_idx"], ref["kept_idx"])
+    for name in ("l0", "r0", "l1", "r1", "l0_ret"):
+        assert np.array_equal(got[name], ref[name]), name
+    assert np.array_equal(got["ages"], fs.ages)
+    assert len(got["kept_idx"]) > 1000
+
+
+def test_empty_and_tiny_inputs(ctx):
+    u = synth.stereo_unit(320, 240, 7, scene="v0")
+    o, s, e = ctx.lk_track(u["l0"], u["r0"], np.zeros((0, 2), np.float32))
+    assert len(o) == 0 and len(s) == 0
+    o, s, e = ctx.lk_track(u["l0"], u["r0"], np.array([[100.5, 80.25]], np.float32))
+    from oracle import cref
+    ro, rs, re = cref.lk_track(u["l0"], u["r0"], np.array([[100.5, 80.25]], np.float32))
+    assert np.array_equal(o, ro) and np.array_equal(s, rs)

@@ -1,0 +1,235 @@
+"""ctypes binding of libvo_b200.so (include/vo_b200.h).
+
+This is plumbing only: it loads the in-tree shared library and exposes each C-ABI entry point
+with numpy buffers.  There is no Python/CPU implementation behind it -- if the library is
+missing or no B200-class GPU is present, the calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvo_b200.so")
+
+VO_OK = 0
+VO_E_INVALID = -1
+VO_E_CUDA = -2
+VO_E_TOO_FEW_POINTS = -3
+VO_E_UNSUPPORTED = -4
+VO_E_CAPACITY = -5
+
+
+class VoParams(C.Structure):
+    _fields_ = [
+        ("fast_threshold", C.c_int), ("fast_nonmax", C.c_int), ("lk_win", C.c_int),
+        ("lk_max_level", C.c_int), ("lk_max_iters", C.c_int), ("lk_epsilon", C.c_double),
+        ("lk_min_eig", C.c_double), ("circ_threshold", C.c_int), ("pnp_iterations", C.c_int),
+        ("pnp_reproj_error", C.c_float), ("pnp_confidence", C.c_double),
+        ("max_features", C.c_int), ("max_units", C.c_int),
+    ]
+
+
+class VoUnit(C.Structure):
+    _fields_ = [
+        ("l0", C.c_void_p), ("r0", C.c_void_p), ("l1", C.c_void_p), ("r1", C.c_void_p),
+        ("pts", C.c_void_p), ("n_pts", C.c_int), ("t_prev", C.c_double * 3),
+    ]
+
+
+class VoUnitResult(C.Structure):
+    _fields_ = [
+        ("n_features", C.c_int), ("n_detected", C.c_int), ("n_tracked", C.c_int), ("n_valid", C.c_int),
+        ("n_inliers", C.c_int), ("ransac_iters", C.c_int), ("pnp_status", C.c_int),
+        ("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("R", C.c_double * 9),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/vo_b200.h declares must be listed here
+SIGNATURES = {
+    "vo_default_params": (None, [C.POINTER(VoParams)]),
+    "vo_create": (C.c_int, [C.c_int, C.POINTER(VoParams), C.POINTER(C.c_void_p)]),
+    "vo_destroy": (None, [C.c_void_p]),
+    "vo_last_error": (C.c_char_p, [C.c_void_p]),
+    "vo_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vo_sync": (C.c_int, [C.c_void_p]),
+    "vo_kernel_launches": (C.c_longlong, [C.c_void_p]),
+    "vo_lk_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
+    "vo_fast_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.POINTER(C.c_int)]),
+    "vo_lk_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vo_circular_match": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                                    C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int)]),
+    "vo_triangulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vo_pnp_ransac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]),
+    "vo_batch_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vo_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(VoUnit), C.c_int, C.c_size_t]),
+    "vo_batch_run": (C.c_int, [C.c_void_p]),
+    "vo_batch_download": (C.c_int, [C.c_void_p, C.POINTER(VoUnitResult), C.c_int]),
+    "vo_frame_batch": (C.c_int, [C.c_void_p, C.POINTER(VoUnit), C.c_int, C.c_size_t, C.POINTER(VoUnitResult)]),
+    "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m visual_odom_b200.build` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name, None)
+            if fn is None:
+                continue            # reported by tests/test_abi.py
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class VoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Context:
+    """Owns one vo_ctx (one per GPU / host thread)."""
+
+    def __init__(self, device=0, **params):
+        self.lib = load_library()
+        p = VoParams()
+        self.lib.vo_default_params(C.byref(p))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown vo_params field {k}")
+            setattr(p, k, v)
+        self.params = p
+        h = C.c_void_p()
+        rc = self.lib.vo_create(device, C.byref(p), C.byref(h))
+        self.h = h
+        if rc != VO_OK:
+            msg = self.lib.vo_last_error(h).decode() if h else "vo_create failed"
+            if h:
+                self.lib.vo_destroy(h)
+            self.h = None
+            raise VoError(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, ok=(VO_OK,)):
+        if rc not in ok:
+            raise VoError(rc, self.lib.vo_last_error(self.h).decode())
+        return rc
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.vo_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(self.lib.vo_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.vo_kernel_launches(self.h))
+
+    def lk_kernel_time(self, reset=False):
+        ms = C.c_double(); n = C.c_longlong()
+        self._check(self.lib.vo_lk_kernel_time(self.h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
+
+    # ---- single-call entry points (host buffers) -------------------------------------------------
+    @staticmethod
+    def _img(a):
+        a = np.asarray(a)
+        assert a.dtype == np.uint8 and a.ndim == 2, "images must be 2-D uint8 (CV_8UC1)"
+        if a.strides[1] != 1:
+            a = np.ascontiguousarray(a)
+        return a
+
+    def fast_detect(self, img, cap=None, with_response=False):
+        img = self._img(img)
+        h, w = img.shape
+        cap = cap or self.params.max_features * 8
+        out = np.zeros((cap, 2), np.float32)
+        resp = np.zeros(cap, np.float32) if with_response else None
+        n = C.c_int()
+        self._check(self.lib.vo_fast_detect(self.h, _p(img), w, h, img.strides[0], _p(out), _p(resp), cap, C.byref(n)),
+                    ok=(VO_OK, VO_E_CAPACITY))
+        m = min(n.value, cap)
+        return (out[:m], resp[:m], n.value) if with_response else (out[:m], n.value)
+
+    def lk_track(self, prev, nxt, pts, want_err=True):
+        prev = self._img(prev); nxt = self._img(nxt)
+        assert prev.shape == nxt.shape and prev.strides == nxt.strides
+        h, w = prev.shape
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        out = np.zeros((n, 2), np.float32); st = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32) if want_err else None
+        self._check(self.lib.vo_lk_track(self.h, _p(prev), _p(nxt), w, h, prev.strides[0], _p(pts), n,
+                                         _p(out), _p(st), _p(err)))
+        return out, st, err
+
+    def circular_match(self, l0, r0, l1, r1, pts, ages=None):
+        imgs = [self._img(a) for a in (l0, r0, l1, r1)]
+        assert all(a.shape == imgs[0].shape and a.strides == imgs[0].strides for a in imgs)
+        h, w = imgs[0].shape
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        outs = [np.zeros((n, 2), np.float32) for _ in range(5)]
+        status4 = np.zeros((4, n), np.uint8)
+        raw4 = np.zeros((4, n, 2), np.float32)
+        kept = np.zeros(n, np.int32)
+        nk = C.c_int()
+        ages_io = None if ages is None else np.ascontiguousarray(ages, np.int32).copy()
+        self._check(self.lib.vo_circular_match(
+            self.h, _p(imgs[0]), _p(imgs[1]), _p(imgs[2]), _p(imgs[3]), w, h, imgs[0].strides[0], _p(pts), n,
+            _p(ages_io), _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _p(outs[4]), _p(status4), _p(raw4),
+            _p(kept), C.byref(nk)))
+        k = nk.value
+        return {
+            "l0": outs[0][:k], "r0": outs[1][:k], "l1": outs[2][:k], "r1": outs[3][:k], "l0_ret": outs[4][:k],
+            "status4": status4, "raw4": raw4, "kept_idx": kept[:k],
+            "ages": None if ages_io is None else ages_io[:k],
+        }
+
+    def triangulate(self, P_l, P_r, pts_l, pts_r):
+        P_l = np.ascontiguousarray(P_l, np.float32).reshape(12); P_r = np.ascontiguousarray(P_r, np.float32).reshape(12)
+        a = np.ascontiguousarray(pts_l, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts_r, np.float32).reshape(-1, 2)
+        assert len(a) == len(b)
+        X = np.zeros((len(a), 3), np.float32)
+        self._check(self.lib.vo_triangulate(self.h, _p(P_l), _p(P_r), _p(a), _p(b), len(a), _p(X)))
+        return X
+
+    def pnp_ransac(self, X, x, K, rvec0=None, tvec0=None):
+        X = np.ascontiguousarray(X, np.float32).reshape(-1, 3); x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)
+        assert len(X) == len(x)
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        rvec = np.zeros(3) if rvec0 is None else np.ascontiguousarray(rvec0, np.float64).reshape(3).copy()
+        tvec = np.zeros(3) if tvec0 is None else np.ascontiguousarray(tvec0, np.float64).reshape(3).copy()
+        inl = np.zeros(max(len(X), 1), np.int32); n_in = C.c_int(); R = np.zeros(9); iters = C.c_int()
+        rc = self.lib.vo_pnp_ransac(self.h, _p(X), _p(x), len(X), _p(K), _p(rvec), _p(tvec), _p(inl), C.byref(n_in),
+                                    _p(R), C.byref(iters))
+        self._check(rc)
+        return {"rvec": rvec, "tvec": tvec, "R": R.reshape(3, 3), "inliers": inl[:n_in.value], "iters": iters.value}

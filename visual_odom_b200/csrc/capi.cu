@@ -1,0 +1,94 @@
+// capi.cu -- extern "C" entry points with HOST buffers (the drop-in boundary, include/vo_b200.h).
+#include "ctx.h"
+#include <string.h>
+
+static int upload_image(vo_ctx* ctx, int plane, const uint8_t* img, int w, int h, size_t pitch)
+{
+    VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_raw + (size_t)plane * w * h, w, img, pitch, w, h,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    return VO_OK;
+}
+
+static int check_common(vo_ctx* ctx, int w, int h, size_t pitch, int n)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (w <= 0 || h <= 0 || pitch < (size_t)w) { vo_set_error(ctx, "bad image geometry %dx%d pitch %zu", w, h, pitch); return VO_E_INVALID; }
+    if (n < 0) { vo_set_error(ctx, "negative point count"); return VO_E_INVALID; }
+    if (n > ctx->cap) { vo_set_error(ctx, "n=%d exceeds context capacity max_features=%d", n, ctx->cap); return VO_E_CAPACITY; }
+    return VO_OK;
+}
+
+extern "C" int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t pitch,
+                           const vo_point2f* prev_pts, int n, vo_point2f* next_pts, uint8_t* status, float* err)
+{
+    int rc = check_common(ctx, w, h, pitch, n);
+    if (rc) return rc;
+    if (n == 0) return VO_OK;          // OpenCV's LK returns early on 0 points
+    if (!prev || !next || !prev_pts || !next_pts || !status) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    rc = vo_ensure_state(ctx, w, h, 1, 2);
+    if (rc) return rc;
+    ctx->imgs_per_unit = 2;
+    if ((rc = upload_image(ctx, 0, prev, w, h, pitch))) return rc;
+    if ((rc = upload_image(ctx, 1, next, w, h, pitch))) return rc;
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in, prev_pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_npts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int ip[1] = {0}, in[1] = {1};
+    rc = vo_run_lk(ctx, 1, 1, ip, in, err != nullptr);
+    ctx->imgs_per_unit = 4;
+    if (rc) return rc;
+    VO_CUDA_CHECK(cudaMemcpyAsync(next_pts, ctx->d_pts_out, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(status, ctx->d_status, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) VO_CUDA_CHECK(cudaMemcpyAsync(err, ctx->d_err, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+extern "C" int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* r0, const uint8_t* l1,
+                                 const uint8_t* r1, int w, int h, size_t pitch, const vo_point2f* pts_l0, int n,
+                                 int32_t* ages_io, vo_point2f* o_l0, vo_point2f* o_r0, vo_point2f* o_l1,
+                                 vo_point2f* o_r1, vo_point2f* o_l0_ret, uint8_t* status4, vo_point2f* raw4,
+                                 int32_t* kept_idx, int* n_kept)
+{
+    int rc = check_common(ctx, w, h, pitch, n);
+    if (rc) return rc;
+    if (n_kept) *n_kept = 0;
+    if (n == 0) return VO_OK;
+    if (!l0 || !r0 || !l1 || !r1 || !pts_l0) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    rc = vo_ensure_state(ctx, w, h, 1, 4);
+    if (rc) return rc;
+    ctx->imgs_per_unit = 4;
+    const uint8_t* imgs[4] = {l0, r0, l1, r1};
+    for (int i = 0; i < 4; i++)
+        if ((rc = upload_image(ctx, i, imgs[i], w, h, pitch))) return rc;
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in, pts_l0, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_npts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (ages_io)
+        VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_ages_in, ages_io, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    // ring order: L0->R0, R0->R1, R1->L1, L1->L0   (planes: L0=0, R0=1, L1=2, R1=3)
+    const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};
+    if ((rc = vo_run_lk(ctx, 1, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, 1, ages_io != nullptr))) return rc;
+    int n3 = 0;
+    VO_CUDA_CHECK(cudaMemcpyAsync(&n3, ctx->d_n3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    if (status4)
+        for (int c = 0; c < 4; c++)
+            VO_CUDA_CHECK(cudaMemcpyAsync(status4 + (size_t)c * n, ctx->d_status + c * cs, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (raw4)
+        for (int c = 0; c < 4; c++)
+            VO_CUDA_CHECK(cudaMemcpyAsync(raw4 + (size_t)c * n, ctx->d_pts_out + c * cs, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // n3 is needed to size the remaining copies
+    vo_point2f* outs[5] = {o_l0, o_r0, o_l1, o_r1, o_l0_ret};
+    for (int k = 0; k < 5; k++)
+        if (outs[k] && n3 > 0)
+            VO_CUDA_CHECK(cudaMemcpyAsync(outs[k], ctx->d_kept5 + k * cs, (size_t)n3 * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (kept_idx && n3 > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(kept_idx, ctx->d_idx3, (size_t)n3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ages_io && n3 > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(ages_io, ctx->d_ages_out, (size_t)n3 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (n_kept) *n_kept = n3;
+    return VO_OK;
+}

@@ -1,0 +1,314 @@
+// ctx.cu -- context life-cycle, device state, TMA descriptor encoding, stage runners.
+#include "ctx.h"
+#include <string.h>
+#include <stdlib.h>
+
+void vo_set_error(vo_ctx* ctx, const char* fmt, ...)
+{
+    if (!ctx) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" void vo_default_params(vo_params* p)
+{
+    p->fast_threshold = 20;
+    p->fast_nonmax = 1;
+    p->lk_win = 21;
+    p->lk_max_level = 3;
+    p->lk_max_iters = 30;
+    p->lk_epsilon = 0.01;
+    p->lk_min_eig = 0.001;
+    p->circ_threshold = 0;
+    p->pnp_iterations = 500;
+    p->pnp_reproj_error = 0.5f;
+    p->pnp_confidence = 0.999;
+    p->max_features = 8192;
+    p->max_units = 1;
+}
+
+extern "C" int vo_create(int device, const vo_params* params, vo_ctx** out)
+{
+    if (!out) return VO_E_INVALID;
+    *out = nullptr;
+    vo_ctx* ctx = new vo_ctx();
+    if (params) ctx->p = *params; else vo_default_params(&ctx->p);
+    ctx->device = device;
+    *out = ctx;      // returned even on failure so the caller can read vo_last_error()
+    if (ctx->p.lk_win != VO_WIN) {
+        vo_set_error(ctx, "lk_win=%d unsupported: the LK kernel is built for the reference's 21x21 window", ctx->p.lk_win);
+        return VO_E_UNSUPPORTED;
+    }
+    if (ctx->p.lk_max_level < 0 || ctx->p.lk_max_level >= VO_MAX_LEVELS) {
+        vo_set_error(ctx, "lk_max_level=%d outside [0,%d]", ctx->p.lk_max_level, VO_MAX_LEVELS - 1);
+        return VO_E_UNSUPPORTED;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        vo_set_error(ctx, "no CUDA device available (%s): this library has no CPU fallback", cudaGetErrorString(e));
+        return VO_E_CUDA;
+    }
+    VO_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VO_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        vo_set_error(ctx, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        return VO_E_UNSUPPORTED;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    VO_CUDA_CHECK(vo_lk_prepare());
+    ctx->cap = ctx->p.max_features;
+    return VO_OK;
+}
+
+extern "C" void vo_destroy(vo_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    vo_free_state(ctx);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char* vo_last_error(const vo_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int vo_set_stream(vo_ctx* ctx, void* s)
+{
+    if (!ctx) return VO_E_INVALID;
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return VO_OK;
+}
+
+extern "C" int vo_sync(vo_ctx* ctx)
+{
+    if (!ctx) return VO_E_INVALID;
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+extern "C" long long vo_kernel_launches(const vo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset)
+{
+    if (!ctx) return VO_E_INVALID;
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0.f;
+        VO_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+        ctx->lk_ms += ms;
+        ctx->lk_n++;
+    }
+    ctx->ev_used = 0;
+    if (ms_total) *ms_total = ctx->lk_ms;
+    if (n) *n = ctx->lk_n;
+    if (reset) { ctx->lk_ms = 0.0; ctx->lk_n = 0; }
+    return VO_OK;
+}
+
+int vo_ensure_pinned(vo_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_pinned_bytes) return VO_OK;
+    if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; }
+    VO_CUDA_CHECK(cudaMallocHost(&ctx->h_pinned, bytes));
+    ctx->h_pinned_bytes = bytes;
+    return VO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+void vo_free_state(vo_ctx* ctx)
+{
+    for (void* p : ctx->allocs) cudaFree(p);
+    ctx->allocs.clear();
+    ctx->w = ctx->h = ctx->units = 0;
+}
+
+template <typename T>
+static cudaError_t dalloc(vo_ctx* ctx, T** p, size_t count)
+{
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e == cudaSuccess) { ctx->allocs.push_back(q); *p = (T*)q; }
+    return e;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_maps(vo_ctx* ctx)
+{
+    // resolved through the runtime so that the .so does not link libcuda (it must load on CPU-only hosts)
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VO_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        vo_set_error(ctx, "cuTensorMapEncodeTiled not available from the driver");
+        return VO_E_CUDA;
+    }
+    PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+    const int n_img = ctx->units * 4;
+    for (int l = 0; l < ctx->pg.nlevels; l++) {
+        const LevelGeom& g = ctx->pg.lv[l];
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.hp, (cuuint64_t)n_img};
+            cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane};
+            cuuint32_t box[3] = {32, 32, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(&ctx->maps.img[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { vo_set_error(ctx, "cuTensorMapEncodeTiled(u8 level %d) failed: %d", l, (int)r); return VO_E_CUDA; }
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.hp, (cuuint64_t)n_img};
+            cuuint64_t strides[2] = {(cuuint64_t)g.pitch * 4, (cuuint64_t)g.plane * 4};
+            cuuint32_t box[3] = {24, 22, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(&ctx->maps.der[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, g.der, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { vo_set_error(ctx, "cuTensorMapEncodeTiled(deriv level %d) failed: %d", l, (int)r); return VO_E_CUDA; }
+        }
+    }
+    return VO_OK;
+}
+
+int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
+{
+    if (w <= 0 || h <= 0 || units <= 0) { vo_set_error(ctx, "bad geometry %dx%d units=%d", w, h, units); return VO_E_INVALID; }
+    if (ctx->w == w && ctx->h == h && ctx->units >= units) return VO_OK;
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    vo_free_state(ctx);
+    const int n_img = units * 4;
+    const int cap = ctx->cap;
+    // pyramid geometry: OpenCV stops adding levels once a level is not larger than the window
+    PyrGeom& pg = ctx->pg;
+    memset(&pg, 0, sizeof(pg));
+    int cw = w, ch = h;
+    for (int l = 0; l <= ctx->p.lk_max_level; l++) {
+        if (l > 0) {
+            int nw = (cw + 1) / 2, nh = (ch + 1) / 2;
+            if (nw <= VO_WIN || nh <= VO_WIN) break;
+            cw = nw; ch = nh;
+        }
+        LevelGeom& g = pg.lv[l];
+        g.w = cw; g.h = ch;
+        g.pitch = ((cw + 2 * VO_PAD) + 63) / 64 * 64;
+        g.hp = ch + 2 * VO_PAD;
+        g.plane = (size_t)g.pitch * g.hp;
+        VO_CUDA_CHECK(dalloc(ctx, &g.img, g.plane * n_img));
+        VO_CUDA_CHECK(dalloc(ctx, &g.der, g.plane * n_img));
+        VO_CUDA_CHECK(cudaMemsetAsync(g.img, 0, g.plane * n_img, ctx->stream));
+        VO_CUDA_CHECK(cudaMemsetAsync(g.der, 0, g.plane * n_img * sizeof(uint32_t), ctx->stream));
+        pg.nlevels = l + 1;
+    }
+    pg.n_img = n_img;
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_raw, (size_t)n_img * w * h));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_raw_tab, (size_t)n_img));
+    {
+        std::vector<const uint8_t*> tab(n_img);
+        for (int i = 0; i < n_img; i++) tab[i] = ctx->d_raw + (size_t)i * w * h;
+        VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_raw_tab, tab.data(), n_img * sizeof(uint8_t*), cudaMemcpyHostToDevice, ctx->stream));
+        VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    const size_t uc = (size_t)units * cap;
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_pts_in, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_npts, (size_t)units));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_pts_out, 4 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_status, 4 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_err, 4 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_ages_in, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_ages_out, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_kept5, 5 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_idx3, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_n3, (size_t)units));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_valid4, 4 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_idx5, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_n5, (size_t)units));
+    ctx->w = w; ctx->h = h; ctx->units = units;
+    int rc = encode_maps(ctx);
+    if (rc != VO_OK) { vo_free_state(ctx); return rc; }
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int* img_next, bool want_err)
+{
+    PyrGeom pg = ctx->pg;
+    pg.n_img = units * ctx->imgs_per_unit;
+    ctx->launches += vo_launch_pyramid(pg, ctx->d_raw_tab, ctx->w, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+
+    LkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_units = units;
+    a.cap = ctx->cap;
+    a.n_pts = ctx->d_npts;
+    a.imgs_per_unit = ctx->imgs_per_unit;
+    a.ncalls = ncalls;
+    for (int c = 0; c < ncalls; c++) { a.img_prev[c] = img_prev[c]; a.img_next[c] = img_next[c]; }
+    a.nlevels = pg.nlevels;
+    for (int l = 0; l < pg.nlevels; l++) { a.lw[l] = pg.lv[l].w; a.lh[l] = pg.lv[l].h; }
+    a.max_iters = ctx->p.lk_max_iters;
+    double eps = ctx->p.lk_epsilon;
+    if (eps < 0.) eps = 0.; if (eps > 10.) eps = 10.;
+    a.eps2 = eps * eps;
+    a.min_eig = ctx->p.lk_min_eig;
+    a.pts_in = ctx->d_pts_in;
+    a.pts_out = ctx->d_pts_out;
+    a.status_out = ctx->d_status;
+    a.err_out = want_err ? ctx->d_err : nullptr;
+    a.call_stride = (size_t)ctx->units * ctx->cap;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->lk_timing) {
+        if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+            cudaEvent_t a0, a1;
+            VO_CUDA_CHECK(cudaEventCreate(&a0));
+            VO_CUDA_CHECK(cudaEventCreate(&a1));
+            ctx->ev_pool.push_back(a0); ctx->ev_pool.push_back(a1);
+        }
+        e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
+        ctx->ev_used += 2;
+        VO_CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+    }
+    VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->stream));
+    ctx->launches += 1;
+    if (e1) VO_CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+    return VO_OK;
+}
+
+int vo_run_filter(vo_ctx* ctx, int units, bool with_ages)
+{
+    FilterArgs f;
+    memset(&f, 0, sizeof(f));
+    f.cap = ctx->cap;
+    f.call_stride = (size_t)ctx->units * ctx->cap;
+    f.circ_threshold = ctx->p.circ_threshold;
+    f.n_pts = ctx->d_npts;
+    f.pts_in = ctx->d_pts_in;
+    f.pts_out = ctx->d_pts_out;
+    f.status = ctx->d_status;
+    f.ages_in = with_ages ? ctx->d_ages_in : nullptr;
+    f.ages_out = ctx->d_ages_out;
+    f.kept5 = ctx->d_kept5;
+    f.idx3 = ctx->d_idx3;
+    f.n3 = ctx->d_n3;
+    f.valid4 = ctx->d_valid4;
+    f.idx5 = ctx->d_idx5;
+    f.n5 = ctx->d_n5;
+    VO_CUDA_CHECK(vo_launch_ring_filter(f, units, ctx->stream));
+    ctx->launches += 1;
+    return VO_OK;
+}

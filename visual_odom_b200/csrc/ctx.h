@@ -1,0 +1,64 @@
+// ctx.h -- the library context (device-resident state shared by every entry point)
+#pragma once
+#include "common.cuh"
+#include "lk_ring.h"
+#include "filter.h"
+#include "../../include/vo_b200.h"
+#include <vector>
+#include <stdarg.h>
+
+struct vo_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    vo_params p;
+    char err[1024] = {0};
+    long long launches = 0;
+    int sm_count = 0;
+
+    // ---- geometry of the currently allocated batch state -----------------------------------
+    int w = 0, h = 0;             // image size
+    int units = 0;                // allocated work-unit slots
+    int imgs_per_unit = 4;
+    int cap = 0;                  // feature capacity per unit
+    PyrGeom pg;                   // device plane pointers per level
+    LkMaps maps;                  // TMA descriptors per level
+    bool have_P = false;
+    float P_l[12], P_r[12];
+
+    // ---- device buffers ---------------------------------------------------------------------
+    uint8_t* d_raw = nullptr;           // [units*4][h*w] raw images
+    const uint8_t** d_raw_tab = nullptr;// [units*4] pointers into d_raw (or caller device images)
+    float2* d_pts_in = nullptr;         // [units][cap]
+    int* d_npts = nullptr;              // [units]
+    float2* d_pts_out = nullptr;        // [4][units][cap]
+    uint8_t* d_status = nullptr;        // [4][units][cap]
+    float* d_err = nullptr;             // [4][units][cap]
+    int* d_ages_in = nullptr;           // [units][cap]
+    int* d_ages_out = nullptr;          // [units][cap]
+    float2* d_kept5 = nullptr;          // [5][units][cap]
+    int* d_idx3 = nullptr;              // [units][cap]
+    int* d_n3 = nullptr;                // [units]
+    float2* d_valid4 = nullptr;         // [4][units][cap]
+    int* d_idx5 = nullptr;              // [units][cap]
+    int* d_n5 = nullptr;                // [units]
+    std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
+
+    // ---- pinned host staging ------------------------------------------------------------------
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+
+    // ---- LK kernel timing (CUDA events on the launching stream) -------------------------------
+    std::vector<cudaEvent_t> ev_pool;   // pairs: start, stop
+    size_t ev_used = 0;
+    double lk_ms = 0.0;
+    long long lk_n = 0;
+    bool lk_timing = true;
+};
+
+void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
+int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
+void vo_free_state(vo_ctx* ctx);
+int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
+// run pyramids + LK (ncalls chained) for `units` units; images must already be in d_raw/d_raw_tab
+int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int* img_next, bool want_err);
+int vo_run_filter(vo_ctx* ctx, int units, bool with_ages);

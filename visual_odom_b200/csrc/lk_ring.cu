@@ -1,0 +1,416 @@
+// lk_ring.cu -- K2: the pyramidal Lucas-Kanade kernel (the hot kernel of this library).
+//
+// Replaces the four chained cv::calcOpticalFlowPyrLK calls of the reference's circularMatching()
+// (reference src/feature.cpp:136-139; window 21x21 :127, 30 iterations / eps 0.01 :128,
+// maxLevel 3, minEigThreshold 1e-3 :136).  Arithmetic restated in oracle/lk_ref.c (lk_track),
+// which is pinned bit-for-bit against cv2 4.13.0; this kernel reproduces the same bits:
+//   * fixed-point bilinear patches (weights cvRound(w*2^14), DESCALE by 9 / 14)
+//   * float32 normal equations accumulated in OpenCV's 4-SIMD-lane + scalar-tail order
+//     (the order matters once partial sums pass 2^24; see "summation chains" below)
+//   * per-level next = next*2 propagation, level-0-only status writes, final bounds re-check.
+//
+// Parallelisation: ONE WARP PER FEATURE, and one launch runs the WHOLE ring (up to 4 chained
+// calls x all pyramid levels) for every feature of every unit -- a feature's track never
+// depends on another feature, so nothing forces a launch boundary between levels or calls.
+//
+// Staging: per level, lane 0 issues three TMA (cp.async.bulk.tensor.3d) box loads into the
+// warp's private shared memory: the 32x32 u8 window of the previous image, the 24x22 s16x2
+// window of its Scharr derivative, and a 32x32 u8 tile of the next image around the current
+// estimate (re-issued only if the 22x22 search window drifts out of the tile).  The planes are
+// physically padded (see common.cuh), so no box ever needs border handling.
+//
+// Summation chains: OpenCV accumulates A11/A12/A22 and b1/b2 in float32 with 4 SIMD lanes over
+// columns 0..15 (lane = x & 3) and a scalar tail over columns 16..20, rows outermost.  The 441
+// window pixels are therefore split into 5 ordered chains (4 x 84 + 105 pixels).  Lanes 0..23
+// own the four SIMD chains (6 lanes x 14 consecutive chain elements), lanes 24..31 own the tail
+// (8 lanes x 14).  All addends are integers, so when the sum of |addend| over a chain is
+// <= 2^24 every partial sum is exact and the chain total is order independent: that fast path
+// uses integer shuffles.  Otherwise the chain is replayed faithfully: lane s adds its 14
+// elements in order and hands the running float to lane s+1.
+#include "common.cuh"
+#include "lk_ring.h"
+
+#define FULL 0xffffffffu
+#define W_BITS 14
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// per-warp shared memory
+struct __align__(128) WarpSmem {
+    uint8_t iwin[32 * 32];      // previous-image window rows 0..21 used (box 32 x 32)
+    uint8_t jtile[32 * 32];     // next-image tile
+    uint32_t dwin[24 * 22 + 16];// derivative window (box 24 x 22 uint32) (+pad to keep 128B multiple)
+    uint64_t bar;               // mbarrier for TMA completion
+    uint64_t pad_[15];
+};
+static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep 128B alignment");
+
+#define I_BYTES (32 * 32)
+#define J_BYTES (32 * 32)
+#define D_BYTES (24 * 22 * 4)
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    w00 = __float2int_rn((1.f - a) * (1.f - b) * (float)(1 << W_BITS));
+    w01 = __float2int_rn(a * (1.f - b) * (float)(1 << W_BITS));
+    w10 = __float2int_rn((1.f - a) * b * (float)(1 << W_BITS));
+    w11 = (1 << W_BITS) - w00 - w01 - w10;
+}
+
+// tree reduction over the lanes of one chain group (6 or 8 consecutive lanes), result at sub==0
+__device__ __forceinline__ int group_sum(int v, int sub, int gsize)
+{
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        int o = __shfl_down_sync(FULL, v, d);
+        if (sub + d < gsize) v += o;
+    }
+    return v;
+}
+
+// faithful float chain: every lane holds `cnt` addends v[0..cnt) of its chain segment;
+// returns the chain total in the LAST lane of each group (sub == gsize-1).
+template <int NV>
+__device__ __forceinline__ float chain_sum(const float (&v)[NV], int cnt, int sub)
+{
+    float acc = 0.f;
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        float up = __shfl_up_sync(FULL, acc, 1);
+        if (sub == r) {
+            acc = (r == 0) ? 0.f : up;
+#pragma unroll
+            for (int k = 0; k < NV; k++)
+                if (k < cnt) acc = __fadd_rn(acc, v[k]);
+        }
+    }
+    return acc;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32)
+k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp_in_cta];
+
+    const int gwarp = blockIdx.x * LK_WARPS_PER_CTA + warp_in_cta;
+    const int unit = gwarp / args.cap;
+    const int f = gwarp - unit * args.cap;
+    if (unit >= args.n_units) return;
+    const int npts = args.n_pts ? args.n_pts[unit] : args.cap;
+    if (f >= npts) return;
+
+    // static lane -> chain-element assignment
+    const bool tail = lane >= 24;
+    const int chain = tail ? 4 : lane / 6;
+    const int sub = tail ? lane - 24 : lane - chain * 6;
+    const int gsize = tail ? 8 : 6;
+    const int e0 = sub * 14;                       // first chain element of this lane
+    const int nel = tail ? (105 - e0 < 14 ? 105 - e0 : 14) : 14;   // elements owned (tail last lane: 7)
+    // element k -> (row, col) in the 21x21 window; pre-compute window offsets (row*32+col)
+    int woff[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+        int e = e0 + k, row, col;
+        if (tail) { row = e / 5; col = 16 + e - row * 5; }
+        else { row = e >> 2; col = chain + 4 * (e & 3); }
+        if (k >= nel) { row = 0; col = 0; }
+        woff[k] = row * 32 + col;
+    }
+
+    if (lane == 0) {
+        mbar_init(&sm.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+
+    const size_t pbase = (size_t)unit * args.cap + f;
+    float2 pt = args.pts_in[pbase];
+    const float half = (VO_WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int max_level = args.nlevels - 1;
+
+    for (int call = 0; call < args.ncalls; call++) {
+        const int img_prev = unit * args.imgs_per_unit + args.img_prev[call];
+        const int img_next = unit * args.imgs_per_unit + args.img_next[call];
+        float2 nxt = make_float2(0.f, 0.f);
+        int status = 1;
+        float errv = 0.f;
+
+        for (int level = max_level; level >= 0; level--) {
+            const int lw = args.lw[level], lh = args.lh[level];
+            const float sc = 1.f / (float)(1 << level);
+            float px = pt.x * sc, py = pt.y * sc;
+            if (level == max_level) { nxt.x = px; nxt.y = py; }
+            else { nxt.x = nxt.x * 2.f; nxt.y = nxt.y * 2.f; }
+            px -= half; py -= half;
+            const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+            if (ipx < -VO_WIN || ipx >= lw || ipy < -VO_WIN || ipy >= lh) {
+                if (level == 0) { status = 0; errv = 0.f; }
+                continue;
+            }
+            // ---- stage windows: I (u8), dI (s16x2), J tile (u8) --------------------------------
+            float npx = nxt.x - half, npy = nxt.y - half;
+            int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
+            const bool j_ok0 = !(inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh);
+            int jox = inx - 5, joy = iny - 5;           // tile origin (image coords)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(&sm.bar, I_BYTES + D_BYTES + (j_ok0 ? J_BYTES : 0));
+                tma_load_3d(sm.iwin, &maps.img[level], &sm.bar, ipx + VO_PAD, ipy + VO_PAD, img_prev);
+                tma_load_3d(sm.dwin, &maps.der[level], &sm.bar, ipx + VO_PAD, ipy + VO_PAD, img_prev);
+                if (j_ok0)
+                    tma_load_3d(sm.jtile, &maps.img[level], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+            }
+            float a = px - (float)ipx, b = py - (float)ipy;
+            int w00, w01, w10, w11;
+            bilinear_weights(a, b, w00, w01, w10, w11);
+            mbar_wait(&sm.bar, phase); phase ^= 1;
+
+            // ---- patch extraction: I (x32), Ix, Iy for the 14 owned elements ------------------
+            short Iv[14];
+            int dxy[14];          // lo16 = Ix, hi16 = Iy (as packed shorts)
+            float A11, A12, A22;
+            {
+                float f11[14], f12[14], f22[14];
+#pragma unroll
+                for (int k = 0; k < 14; k++) {
+                    const uint8_t* s0 = sm.iwin + woff[k];
+                    int ival = (s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
+                    const int drow = woff[k] >> 5, dcol = woff[k] & 31;
+                    const uint32_t* d0 = sm.dwin + drow * 24 + dcol;
+                    uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[24], d11 = d0[25];
+                    int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
+                              (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    int iy = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 +
+                              ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    Iv[k] = (short)ival;
+                    dxy[k] = (ix & 0xffff) | (iy << 16);
+                    float fx = (float)ix, fy = (float)iy;
+                    f11[k] = __fmul_rn(fx, fx); f12[k] = __fmul_rn(fx, fy); f22[k] = __fmul_rn(fy, fy);
+                }
+                // faithful chains (A sums pass 2^24 for any corner-like texture, so no fast path here)
+                float c11 = chain_sum(f11, nel, sub);
+                float c12 = chain_sum(f12, nel, sub);
+                float c22 = chain_sum(f22, nel, sub);
+                // chain totals live in lanes 5, 11, 17, 23 (SIMD lanes 0..3) and 31 (tail)
+                float q0, q1, q2, q3, t;
+                q0 = __shfl_sync(FULL, c11, 5); q1 = __shfl_sync(FULL, c11, 11); q2 = __shfl_sync(FULL, c11, 17);
+                q3 = __shfl_sync(FULL, c11, 23); t = __shfl_sync(FULL, c11, 31);
+                float iA11 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+                q0 = __shfl_sync(FULL, c12, 5); q1 = __shfl_sync(FULL, c12, 11); q2 = __shfl_sync(FULL, c12, 17);
+                q3 = __shfl_sync(FULL, c12, 23); t = __shfl_sync(FULL, c12, 31);
+                float iA12 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+                q0 = __shfl_sync(FULL, c22, 5); q1 = __shfl_sync(FULL, c22, 11); q2 = __shfl_sync(FULL, c22, 17);
+                q3 = __shfl_sync(FULL, c22, 23); t = __shfl_sync(FULL, c22, 31);
+                float iA22 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+                A11 = __fmul_rn(iA11, FLT_SCALE); A12 = __fmul_rn(iA12, FLT_SCALE); A22 = __fmul_rn(iA22, FLT_SCALE);
+            }
+            float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+            {
+                float dd = __fsub_rn(A11, A22);
+                float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+                float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * VO_WIN * VO_WIN));
+                if ((double)minEig < args.min_eig || D < 1.1920928955078125e-07f) {
+                    if (level == 0) status = 0;
+                    continue;
+                }
+            }
+            D = __fdiv_rn(1.f, D);
+
+            // ---- Newton iterations ------------------------------------------------------------
+            float pdx = 0.f, pdy = 0.f;
+            bool tile_valid = j_ok0;
+            for (int j = 0; j < args.max_iters; j++) {
+                inx = __float2int_rd(npx); iny = __float2int_rd(npy);
+                if (inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh) {
+                    if (level == 0) status = 0;
+                    break;
+                }
+                int rx = inx - jox, ry = iny - joy;       // window origin inside the tile
+                if (!tile_valid || rx < 0 || ry < 0 || rx > 32 - 22 || ry > 32 - 22) {
+                    jox = inx - 5; joy = iny - 5; rx = 5; ry = 5;
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(&sm.bar, J_BYTES);
+                        tma_load_3d(sm.jtile, &maps.img[level], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+                    }
+                    mbar_wait(&sm.bar, phase); phase ^= 1;
+                    tile_valid = true;
+                }
+                a = npx - (float)inx; b = npy - (float)iny;
+                bilinear_weights(a, b, w00, w01, w10, w11);
+                const uint8_t* jb = sm.jtile + ry * 32 + rx;
+                int pxv[14], pyv[14];
+                int sx = 0, sy = 0;
+                unsigned ax = 0, ay = 0;
+#pragma unroll
+                for (int k = 0; k < 14; k++) {
+                    const uint8_t* s0 = jb + woff[k];
+                    int diff = ((s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
+                    if (k >= nel) diff = 0;
+                    int vx = diff * (int)(short)(dxy[k] & 0xffff);
+                    int vy = diff * (dxy[k] >> 16);
+                    pxv[k] = vx; pyv[k] = vy;
+                    sx += vx; sy += vy;
+                    ax += (unsigned)abs(vx); ay += (unsigned)abs(vy);
+                }
+                // per-chain totals (exact integers) and per-chain sum of |addend|
+                int csx = group_sum(sx, sub, gsize), csy = group_sum(sy, sub, gsize);
+                int cax = group_sum((int)ax, sub, gsize), cay = group_sum((int)ay, sub, gsize);
+                // NOTE |addend| of the SIMD chains is |pair sum| <= |v0|+|v1|, so the bound is conservative
+                const bool exact = __all_sync(FULL, (sub != 0) || ((unsigned)cax <= (1u << 24) && (unsigned)cay <= (1u << 24)));
+                float fx, fy;      // chain totals as float, valid in lane sub==0 (fast) / sub==gsize-1 (slow)
+                int src_base;
+                if (exact) {
+                    fx = (float)csx; fy = (float)csy; src_base = 0;
+                } else {
+                    float vx[14], vy[14];
+                    int cnt;
+                    if (!tail) {
+#pragma unroll
+                        for (int k = 0; k < 7; k++) {
+                            vx[k] = (float)(pxv[2 * k] + pxv[2 * k + 1]);
+                            vy[k] = (float)(pyv[2 * k] + pyv[2 * k + 1]);
+                        }
+#pragma unroll
+                        for (int k = 7; k < 14; k++) { vx[k] = 0.f; vy[k] = 0.f; }
+                        cnt = 7;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 14; k++) { vx[k] = (float)pxv[k]; vy[k] = (float)pyv[k]; }
+                        cnt = nel;
+                    }
+                    fx = chain_sum(vx, cnt, sub);
+                    fy = chain_sum(vy, cnt, sub);
+                    src_base = -1;   // totals at the last lane of each group
+                }
+                const int l0 = src_base == 0 ? 0 : 5, l1 = src_base == 0 ? 6 : 11, l2 = src_base == 0 ? 12 : 17,
+                          l3 = src_base == 0 ? 18 : 23, lt = src_base == 0 ? 24 : 31;
+                float q0 = __shfl_sync(FULL, fx, l0), q1 = __shfl_sync(FULL, fx, l1), q2 = __shfl_sync(FULL, fx, l2),
+                      q3 = __shfl_sync(FULL, fx, l3), t = __shfl_sync(FULL, fx, lt);
+                // qb0 = [c0, ., c1, .], qb1 = [c2, ., c3, .]; s = qb0+qb1; ib = tail + ((s0 + 0) + (s2 + 0))
+                float ib1 = __fadd_rn(t, __fadd_rn(__fadd_rn(__fadd_rn(q0, q2), 0.f), __fadd_rn(__fadd_rn(q1, q3), 0.f)));
+                q0 = __shfl_sync(FULL, fy, l0); q1 = __shfl_sync(FULL, fy, l1); q2 = __shfl_sync(FULL, fy, l2);
+                q3 = __shfl_sync(FULL, fy, l3); t = __shfl_sync(FULL, fy, lt);
+                float ib2 = __fadd_rn(t, __fadd_rn(__fadd_rn(__fadd_rn(q0, q2), 0.f), __fadd_rn(__fadd_rn(q1, q3), 0.f)));
+
+                float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
+                float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+                float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+                npx = __fadd_rn(npx, dx); npy = __fadd_rn(npy, dy);
+                nxt.x = __fadd_rn(npx, half); nxt.y = __fadd_rn(npy, half);
+                if ((double)dx * (double)dx + (double)dy * (double)dy <= args.eps2) break;
+                if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                    nxt.x = __fsub_rn(nxt.x, __fmul_rn(dx, 0.5f));
+                    nxt.y = __fsub_rn(nxt.y, __fmul_rn(dy, 0.5f));
+                    break;
+                }
+                pdx = dx; pdy = dy;
+            }
+
+            // ---- level 0 epilogue: final bounds re-check (+ err when requested) ---------------
+            if (level == 0 && status) {
+                float fxp = __fsub_rn(nxt.x, half), fyp = __fsub_rn(nxt.y, half);
+                inx = __float2int_rd(fxp); iny = __float2int_rd(fyp);
+                if (inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh) {
+                    status = 0;
+                } else if (args.err_out) {
+                    int rx = inx - jox, ry = iny - joy;
+                    if (!tile_valid || rx < 0 || ry < 0 || rx > 32 - 22 || ry > 32 - 22) {
+                        jox = inx - 5; joy = iny - 5; rx = 5; ry = 5;
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_expect_tx(&sm.bar, J_BYTES);
+                            tma_load_3d(sm.jtile, &maps.img[0], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+                        }
+                        mbar_wait(&sm.bar, phase); phase ^= 1;
+                    }
+                    a = fxp - (float)inx; b = fyp - (float)iny;
+                    bilinear_weights(a, b, w00, w01, w10, w11);
+                    const uint8_t* jb = sm.jtile + ry * 32 + rx;
+                    // errval += |diff| is a plain row-major float sum of small integers
+                    // (<= 441 * 8160 < 2^24): exact, so any order gives the same float.
+                    int s = 0;
+#pragma unroll
+                    for (int k = 0; k < 14; k++) {
+                        const uint8_t* s0 = jb + woff[k];
+                        int diff = ((s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
+                        if (k < nel) s += abs(diff);
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+                    errv = __fdiv_rn(__fmul_rn((float)s, 1.f), (float)(32 * VO_WIN * VO_WIN));
+                }
+            }
+        } // level
+
+        if (lane == 0) {
+            const size_t o = (size_t)call * args.call_stride + pbase;
+            args.pts_out[o] = nxt;
+            args.status_out[o] = (uint8_t)status;
+            if (args.err_out) args.err_out[o] = errv;
+        }
+        pt = nxt;
+    } // call
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t vo_lk_smem_bytes() { return sizeof(WarpSmem) * LK_WARPS_PER_CTA; }
+
+cudaError_t vo_lk_prepare()
+{
+    return cudaFuncSetAttribute(k_lk_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vo_lk_smem_bytes());
+}
+
+cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, cudaStream_t stream)
+{
+    const long warps = (long)args.n_units * args.cap;
+    if (warps <= 0) return cudaSuccess;
+    const int ctas = (int)((warps + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA);
+    k_lk_ring<<<ctas, LK_WARPS_PER_CTA * 32, vo_lk_smem_bytes(), stream>>>(maps, args);
+    return cudaGetLastError();
+}

@@ -1,0 +1,35 @@
+// lk_ring.h -- launch interface of the LK ring kernel (lk_ring.cu)
+#pragma once
+#include "common.cuh"
+
+#define LK_WARPS_PER_CTA 8
+
+struct LkMaps {
+    CUtensorMap img[VO_MAX_LEVELS];   // u8 planes, box 32 x 32 x 1
+    CUtensorMap der[VO_MAX_LEVELS];   // s16x2 (uint32) planes, box 24 x 22 x 1
+};
+
+struct LkArgs {
+    int n_units;            // work units in this launch
+    int cap;                // feature capacity per unit (stride of the point arrays)
+    const int* n_pts;       // [n_units] live feature count per unit (device) or nullptr = cap
+    int imgs_per_unit;      // planes per unit in the pyramid (4 for the ring, 2 for a single call)
+    int ncalls;             // chained calcOpticalFlowPyrLK calls (4 for the ring)
+    int img_prev[4];        // plane index (within the unit) of prev image per call
+    int img_next[4];        // plane index of next image per call
+    int nlevels;            // pyramid images (effective maxLevel + 1)
+    int lw[VO_MAX_LEVELS], lh[VO_MAX_LEVELS];
+    int max_iters;          // 30
+    double eps2;            // epsilon^2 (0.01^2)
+    double min_eig;         // 1e-3
+    const float2* pts_in;   // [n_units][cap]
+    float2* pts_out;        // [ncalls][n_units][cap]   (call_stride = n_units*cap)
+    uint8_t* status_out;    // [ncalls][n_units][cap]
+    float* err_out;         // optional, same shape
+    size_t call_stride;
+};
+
+size_t vo_lk_smem_bytes();
+cudaError_t vo_lk_prepare();
+cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
+int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch, cudaStream_t stream);

@@ -1,0 +1,137 @@
+// pyramid.cu -- K1: padded u8 Gaussian pyramid + Scharr derivative pyramid (integer, bit-exact).
+//
+// Replaces cv::buildOpticalFlowPyramid as run inside every cv::calcOpticalFlowPyrLK call of the
+// reference's circularMatching() (reference src/feature.cpp:136-139); arithmetic restated in
+// oracle/lk_ref.c (pyr_down_u8, scharr_deriv) and pinned against cv2 there.
+//
+//   level 0   : raw image -> REFLECT_101 padded plane                       (k_pad_level0)
+//   level l+1 : 5x5 [1 4 6 4 1]^2 / 256 pyrDown of level l, written with its REFLECT_101
+//               border in the same launch (border pixels recompute the reflected interior pixel)
+//   derivative: Scharr of level l (reads the padded plane, so REFLECT_101 at the rim is free),
+//               interior only; the border of the derivative plane stays zero (BORDER_CONSTANT).
+//
+// All of it is HBM/L2-bound byte work: one thread per 4 output pixels, 32-bit stores, rows are
+// 64-byte aligned (pitch % 64 == 0).  No tensor cores (no contraction here).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// raw (pitch = src_pitch) -> padded level 0.  grid.z = image index.
+// src images are addressed through a pointer table (one entry per image).
+__global__ void k_pad_level0(const uint8_t* const* __restrict__ src_tab, int src_pitch,
+                             LevelGeom g)
+{
+    const int img = blockIdx.z;
+    const uint8_t* __restrict__ src = src_tab[img];
+    uint8_t* __restrict__ dst = g.img + (size_t)img * g.plane;
+    const int wq = g.pitch >> 2;                       // 4-pixel groups per padded row
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y;                          // padded row
+    if (q >= wq) return;
+    const int sy = vo_reflect101(Y - VO_PAD, g.h);
+    const uint8_t* srow = src + (size_t)sy * src_pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int X = 4 * q + i;
+        int sx = vo_reflect101(X - VO_PAD, g.w);
+        out |= (uint32_t)__ldg(srow + sx) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)Y * g.pitch + 4 * q) = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One launch per level l:  (a) Scharr derivative of level l (interior),
+//                          (b) if has_next: pyrDown level l -> padded level l+1.
+// grid.x covers max(work_a, work_b) in units of 4 horizontally adjacent output pixels.
+__global__ void k_pyr_level(LevelGeom s, LevelGeom d, int has_next)
+{
+    const int img = blockIdx.z;
+    const uint8_t* __restrict__ sp = s.img + (size_t)img * s.plane + (size_t)VO_PAD * s.pitch + VO_PAD; // pixel (0,0)
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+
+    // (a) derivative of level s: rows [0,h), 4 pixels per thread
+    if (row < s.h) {
+        const int x0 = 4 * q;
+        if (x0 < s.w) {
+            uint32_t* __restrict__ dp = s.der + (size_t)img * s.plane + (size_t)(row + VO_PAD) * s.pitch + VO_PAD;
+            const uint8_t* r0 = sp + (size_t)(row - 1) * s.pitch;
+            const uint8_t* r1 = sp + (size_t)row * s.pitch;
+            const uint8_t* r2 = sp + (size_t)(row + 1) * s.pitch;
+            int t0[6], t1[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                int x = x0 - 1 + i;
+                int a = r0[x], b = r1[x], c = r2[x];
+                t0[i] = (a + c) * 3 + b * 10;
+                t1[i] = c - a;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (x0 + i < s.w) {
+                    int dx = t0[i + 2] - t0[i];
+                    int dy = (t1[i] + t1[i + 2]) * 3 + t1[i + 1] * 10;
+                    dp[x0 + i] = ((uint32_t)(uint16_t)(int16_t)dx) | ((uint32_t)(uint16_t)(int16_t)dy << 16);
+                }
+            }
+        }
+    }
+
+    // (b) pyrDown into padded level d: padded rows [0,hp), 4 pixels per thread
+    if (has_next && row < d.hp) {
+        const int wq = d.pitch >> 2;
+        if (q < wq) {
+            uint8_t* __restrict__ dst = d.img + (size_t)img * d.plane + (size_t)row * d.pitch;
+            const int dy = vo_reflect101(row - VO_PAD, d.h);
+            uint32_t out = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int dx = vo_reflect101(4 * q + i - VO_PAD, d.w);
+                // source taps 2*dx-2..2*dx+2 lie inside [-2, w+1]: the REFLECT_101 border of level s
+                const uint8_t* c = sp + (size_t)(2 * dy - 2) * s.pitch + (2 * dx - 2);
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const uint8_t* r = c + (size_t)j * s.pitch;
+                    int h = r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2];
+                    const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+                    acc += kj * h;
+                }
+                out |= (uint32_t)((acc + 128) >> 8) << (8 * i);
+            }
+            *reinterpret_cast<uint32_t*>(dst + 4 * q) = out;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher: builds all levels for n_img images whose raw pointers are in src_tab (device).
+// Returns the number of kernel launches issued.
+int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch,
+                      cudaStream_t stream)
+{
+    int launches = 0;
+    {
+        const LevelGeom& g = pg.lv[0];
+        dim3 block(128, 1, 1);
+        dim3 grid(((g.pitch >> 2) + block.x - 1) / block.x, g.hp, pg.n_img);
+        k_pad_level0<<<grid, block, 0, stream>>>(src_tab_dev, src_pitch, g);
+        launches++;
+    }
+    for (int l = 0; l < pg.nlevels; l++) {
+        const LevelGeom& s = pg.lv[l];
+        const int has_next = (l + 1 < pg.nlevels);
+        const LevelGeom& d = pg.lv[has_next ? l + 1 : l];
+        int qa = (s.w + 3) / 4, rows = s.h;
+        if (has_next) {
+            int qb = d.pitch >> 2;
+            if (qb > qa) qa = qb;
+            if (d.hp > rows) rows = d.hp;
+        }
+        dim3 block(128, 1, 1);
+        dim3 grid((qa + block.x - 1) / block.x, rows, pg.n_img);
+        k_pyr_level<<<grid, block, 0, stream>>>(s, d, has_next);
+        launches++;
+    }
+    return launches;
+}
