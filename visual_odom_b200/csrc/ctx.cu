@@ -63,6 +63,10 @@ extern "C" int vo_create(int device, const vo_params* params, vo_ctx** out)
     ctx->stream = ctx->own_stream;
     VO_CUDA_CHECK(vo_lk_prepare());
     ctx->cap = ctx->p.max_features;
+    {   // VO_LK_STAGING=ldg switches the LK window staging from TMA to plain loads (debug / A-B runs)
+        const char* st = getenv("VO_LK_STAGING");
+        ctx->lk_use_tma = !(st && strcmp(st, "ldg") == 0);
+    }
     return VO_OK;
 }
 
@@ -161,17 +165,21 @@ static int encode_maps(vo_ctx* ctx)
         {
             cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.hp, (cuuint64_t)n_img};
             cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane};
-            cuuint32_t box[3] = {32, 32, 1};
+            cuuint32_t box_i[3] = {48, 22, 1}, box_j[3] = {48, 32, 1};
             cuuint32_t estr[3] = {1, 1, 1};
-            CUresult r = enc(&ctx->maps.img[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
+            CUresult r = enc(&ctx->maps.img_i[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box_i, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS)
+                r = enc(&ctx->maps.img_j[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box_j, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { vo_set_error(ctx, "cuTensorMapEncodeTiled(u8 level %d) failed: %d", l, (int)r); return VO_E_CUDA; }
         }
         {
             cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.hp, (cuuint64_t)n_img};
             cuuint64_t strides[2] = {(cuuint64_t)g.pitch * 4, (cuuint64_t)g.plane * 4};
-            cuuint32_t box[3] = {24, 22, 1};
+            cuuint32_t box[3] = {28, 22, 1};
             cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = enc(&ctx->maps.der[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, g.der, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -270,6 +278,11 @@ int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int
     a.status_out = ctx->d_status;
     a.err_out = want_err ? ctx->d_err : nullptr;
     a.call_stride = (size_t)ctx->units * ctx->cap;
+    a.use_tma = ctx->lk_use_tma ? 1 : 0;
+    for (int l = 0; l < pg.nlevels; l++) {
+        a.img_base[l] = pg.lv[l].img; a.der_base[l] = pg.lv[l].der;
+        a.pitch[l] = pg.lv[l].pitch; a.plane[l] = pg.lv[l].plane;
+    }
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->lk_timing) {

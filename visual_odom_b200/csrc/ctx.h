@@ -53,6 +53,7 @@ struct vo_ctx {
     double lk_ms = 0.0;
     long long lk_n = 0;
     bool lk_timing = true;
+    bool lk_use_tma = true;
 };
 
 void vo_set_error(vo_ctx* ctx, const char* fmt, ...);

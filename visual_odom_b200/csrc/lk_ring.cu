@@ -73,18 +73,42 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 
 // per-warp shared memory
+// TMA tile loads need a 16-byte aligned global start address, so every box starts at the
+// 16-byte boundary at or below the wanted column and is 16 bytes wider than the data it must hold:
+//   u8 windows  : 48 bytes wide  (<= 15 bytes of lead-in + 22 (I) / 32 (J) bytes of payload)
+//   s16x2 window: 28 elements wide (<= 3 elements of lead-in + 22)
+#define IW 48                   // row pitch of the u8 boxes in shared memory
+#define DW 28                   // row pitch (uint32) of the derivative box
+#define I_ROWS 22
+#define J_ROWS 32
 struct __align__(128) WarpSmem {
-    uint8_t iwin[32 * 32];      // previous-image window rows 0..21 used (box 32 x 32)
-    uint8_t jtile[32 * 32];     // next-image tile
-    uint32_t dwin[24 * 22 + 16];// derivative window (box 24 x 22 uint32) (+pad to keep 128B multiple)
-    uint64_t bar;               // mbarrier for TMA completion
+    uint8_t iwin[IW * I_ROWS + 96];     // previous-image window (box 48 x 22)      1056 -> 1152
+    uint8_t jtile[IW * J_ROWS];         // next-image tile       (box 48 x 32)      1536
+    uint32_t dwin[DW * I_ROWS + 24];    // derivative window     (box 28 x 22 u32)  2464 -> 2560
+    uint64_t bar;                       // mbarrier for TMA completion
     uint64_t pad_[15];
 };
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep 128B alignment");
 
-#define I_BYTES (32 * 32)
-#define J_BYTES (32 * 32)
-#define D_BYTES (24 * 22 * 4)
+#define I_BYTES (IW * I_ROWS)
+#define J_BYTES (IW * J_ROWS)
+#define D_BYTES (DW * I_ROWS * 4)
+
+// plain-load staging of one box (debug / A-B path): rows x row_bytes from a padded plane
+__device__ __forceinline__ void ldg_box_u8(uint8_t* dst, const uint8_t* plane, int pitch, int x, int y, int rows, int lane)
+{
+    const uint8_t* src = plane + (size_t)y * pitch + x;
+    for (int r = 0; r < rows; r++) {
+        dst[r * IW + lane] = __ldg(src + (size_t)r * pitch + lane);
+        if (lane < IW - 32) dst[r * IW + 32 + lane] = __ldg(src + (size_t)r * pitch + 32 + lane);
+    }
+}
+__device__ __forceinline__ void ldg_box_u32(uint32_t* dst, const uint32_t* plane, int pitch, int x, int y, int lane)
+{
+    const uint32_t* src = plane + (size_t)y * pitch + x;
+    if (lane < DW)
+        for (int r = 0; r < I_ROWS; r++) dst[r * DW + lane] = __ldg(src + (size_t)r * pitch + lane);
+}
 
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
 {
@@ -149,15 +173,16 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     const int gsize = tail ? 8 : 6;
     const int e0 = sub * 14;                       // first chain element of this lane
     const int nel = tail ? (105 - e0 < 14 ? 105 - e0 : 14) : 14;   // elements owned (tail last lane: 7)
-    // element k -> (row, col) in the 21x21 window; pre-compute window offsets (row*32+col)
-    int woff[14];
+    // element k -> (row, col) in the 21x21 window; pre-compute box offsets
+    int woff[14], doff[14];
 #pragma unroll
     for (int k = 0; k < 14; k++) {
         int e = e0 + k, row, col;
         if (tail) { row = e / 5; col = 16 + e - row * 5; }
         else { row = e >> 2; col = chain + 4 * (e & 3); }
         if (k >= nel) { row = 0; col = 0; }
-        woff[k] = row * 32 + col;
+        woff[k] = row * IW + col;        // offset in a 48-byte-pitch u8 box
+        doff[k] = row * DW + col;        // offset in the derivative box
     }
 
     if (lane == 0) {
@@ -196,19 +221,32 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
             float npx = nxt.x - half, npy = nxt.y - half;
             int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
             const bool j_ok0 = !(inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh);
-            int jox = inx - 5, joy = iny - 5;           // tile origin (image coords)
+            // box origins in padded-plane coordinates, x snapped down to the 16-byte boundary
+            const int ibx = (ipx + VO_PAD) & ~15, iby = ipy + VO_PAD;       // u8 window of I
+            const int dbx = (ipx + VO_PAD) & ~3;                            // derivative window (4 elements = 16 B)
+            int jbx = (inx - 5 + VO_PAD) & ~15, jby = iny - 5 + VO_PAD;     // tile of J
             __syncwarp();
-            if (lane == 0) {
-                mbar_expect_tx(&sm.bar, I_BYTES + D_BYTES + (j_ok0 ? J_BYTES : 0));
-                tma_load_3d(sm.iwin, &maps.img[level], &sm.bar, ipx + VO_PAD, ipy + VO_PAD, img_prev);
-                tma_load_3d(sm.dwin, &maps.der[level], &sm.bar, ipx + VO_PAD, ipy + VO_PAD, img_prev);
+            if (args.use_tma) {
+                if (lane == 0) {
+                    mbar_expect_tx(&sm.bar, I_BYTES + D_BYTES + (j_ok0 ? J_BYTES : 0));
+                    tma_load_3d(sm.iwin, &maps.img_i[level], &sm.bar, ibx, iby, img_prev);
+                    tma_load_3d(sm.dwin, &maps.der[level], &sm.bar, dbx, iby, img_prev);
+                    if (j_ok0)
+                        tma_load_3d(sm.jtile, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
+                }
+            } else {
+                ldg_box_u8(sm.iwin, args.img_base[level] + args.plane[level] * img_prev, args.pitch[level], ibx, iby, I_ROWS, lane);
+                ldg_box_u32(sm.dwin, args.der_base[level] + args.plane[level] * img_prev, args.pitch[level], dbx, iby, lane);
                 if (j_ok0)
-                    tma_load_3d(sm.jtile, &maps.img[level], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+                    ldg_box_u8(sm.jtile, args.img_base[level] + args.plane[level] * img_next, args.pitch[level], jbx, jby, J_ROWS, lane);
+                __syncwarp();
             }
+            const uint8_t* ib = sm.iwin + (ipx + VO_PAD - ibx);
+            const uint32_t* db = sm.dwin + (ipx + VO_PAD - dbx);
             float a = px - (float)ipx, b = py - (float)ipy;
             int w00, w01, w10, w11;
             bilinear_weights(a, b, w00, w01, w10, w11);
-            mbar_wait(&sm.bar, phase); phase ^= 1;
+            if (args.use_tma) { mbar_wait(&sm.bar, phase); phase ^= 1; }
 
             // ---- patch extraction: I (x32), Ix, Iy for the 14 owned elements ------------------
             short Iv[14];
@@ -218,11 +256,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 float f11[14], f12[14], f22[14];
 #pragma unroll
                 for (int k = 0; k < 14; k++) {
-                    const uint8_t* s0 = sm.iwin + woff[k];
-                    int ival = (s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
-                    const int drow = woff[k] >> 5, dcol = woff[k] & 31;
-                    const uint32_t* d0 = sm.dwin + drow * 24 + dcol;
-                    uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[24], d11 = d0[25];
+                    const uint8_t* s0 = ib + woff[k];
+                    int ival = (s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
+                    const uint32_t* d0 = db + doff[k];
+                    uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[DW], d11 = d0[DW + 1];
                     int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
                               (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
                     int iy = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 +
@@ -270,27 +307,33 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     if (level == 0) status = 0;
                     break;
                 }
-                int rx = inx - jox, ry = iny - joy;       // window origin inside the tile
-                if (!tile_valid || rx < 0 || ry < 0 || rx > 32 - 22 || ry > 32 - 22) {
-                    jox = inx - 5; joy = iny - 5; rx = 5; ry = 5;
+                int rx = inx + VO_PAD - jbx, ry = iny + VO_PAD - jby;   // window origin inside the tile
+                if (!tile_valid || rx < 0 || ry < 0 || rx > IW - 22 || ry > J_ROWS - 22) {
+                    jbx = (inx - 5 + VO_PAD) & ~15; jby = iny - 5 + VO_PAD;
+                    rx = inx + VO_PAD - jbx; ry = 5;
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_expect_tx(&sm.bar, J_BYTES);
-                        tma_load_3d(sm.jtile, &maps.img[level], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+                    if (args.use_tma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&sm.bar, J_BYTES);
+                            tma_load_3d(sm.jtile, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
+                        }
+                        mbar_wait(&sm.bar, phase); phase ^= 1;
+                    } else {
+                        ldg_box_u8(sm.jtile, args.img_base[level] + args.plane[level] * img_next, args.pitch[level], jbx, jby, J_ROWS, lane);
+                        __syncwarp();
                     }
-                    mbar_wait(&sm.bar, phase); phase ^= 1;
                     tile_valid = true;
                 }
                 a = npx - (float)inx; b = npy - (float)iny;
                 bilinear_weights(a, b, w00, w01, w10, w11);
-                const uint8_t* jb = sm.jtile + ry * 32 + rx;
+                const uint8_t* jb = sm.jtile + ry * IW + rx;
                 int pxv[14], pyv[14];
                 int sx = 0, sy = 0;
                 unsigned ax = 0, ay = 0;
 #pragma unroll
                 for (int k = 0; k < 14; k++) {
                     const uint8_t* s0 = jb + woff[k];
-                    int diff = ((s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
+                    int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
                     if (k >= nel) diff = 0;
                     int vx = diff * (int)(short)(dxy[k] & 0xffff);
                     int vy = diff * (dxy[k] >> 16);
@@ -359,26 +402,32 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 if (inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh) {
                     status = 0;
                 } else if (args.err_out) {
-                    int rx = inx - jox, ry = iny - joy;
-                    if (!tile_valid || rx < 0 || ry < 0 || rx > 32 - 22 || ry > 32 - 22) {
-                        jox = inx - 5; joy = iny - 5; rx = 5; ry = 5;
+                    int rx = inx + VO_PAD - jbx, ry = iny + VO_PAD - jby;
+                    if (!tile_valid || rx < 0 || ry < 0 || rx > IW - 22 || ry > J_ROWS - 22) {
+                        jbx = (inx - 5 + VO_PAD) & ~15; jby = iny - 5 + VO_PAD;
+                        rx = inx + VO_PAD - jbx; ry = 5;
                         __syncwarp();
-                        if (lane == 0) {
-                            mbar_expect_tx(&sm.bar, J_BYTES);
-                            tma_load_3d(sm.jtile, &maps.img[0], &sm.bar, jox + VO_PAD, joy + VO_PAD, img_next);
+                        if (args.use_tma) {
+                            if (lane == 0) {
+                                mbar_expect_tx(&sm.bar, J_BYTES);
+                                tma_load_3d(sm.jtile, &maps.img_j[0], &sm.bar, jbx, jby, img_next);
+                            }
+                            mbar_wait(&sm.bar, phase); phase ^= 1;
+                        } else {
+                            ldg_box_u8(sm.jtile, args.img_base[0] + args.plane[0] * img_next, args.pitch[0], jbx, jby, J_ROWS, lane);
+                            __syncwarp();
                         }
-                        mbar_wait(&sm.bar, phase); phase ^= 1;
                     }
                     a = fxp - (float)inx; b = fyp - (float)iny;
                     bilinear_weights(a, b, w00, w01, w10, w11);
-                    const uint8_t* jb = sm.jtile + ry * 32 + rx;
+                    const uint8_t* jb = sm.jtile + ry * IW + rx;
                     // errval += |diff| is a plain row-major float sum of small integers
                     // (<= 441 * 8160 < 2^24): exact, so any order gives the same float.
                     int s = 0;
 #pragma unroll
                     for (int k = 0; k < 14; k++) {
                         const uint8_t* s0 = jb + woff[k];
-                        int diff = ((s0[0] * w00 + s0[1] * w01 + s0[32] * w10 + s0[33] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
+                        int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
                         if (k < nel) s += abs(diff);
                     }
 #pragma unroll

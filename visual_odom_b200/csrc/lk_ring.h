@@ -5,8 +5,9 @@
 #define LK_WARPS_PER_CTA 8
 
 struct LkMaps {
-    CUtensorMap img[VO_MAX_LEVELS];   // u8 planes, box 32 x 32 x 1
-    CUtensorMap der[VO_MAX_LEVELS];   // s16x2 (uint32) planes, box 24 x 22 x 1
+    CUtensorMap img_i[VO_MAX_LEVELS];  // u8 planes, box 48 x 22 x 1 (I window, 16-byte aligned start)
+    CUtensorMap img_j[VO_MAX_LEVELS];  // u8 planes, box 48 x 32 x 1 (J tile)
+    CUtensorMap der[VO_MAX_LEVELS];    // s16x2 (uint32) planes, box 28 x 22 x 1
 };
 
 struct LkArgs {
@@ -27,6 +28,12 @@ struct LkArgs {
     uint8_t* status_out;    // [ncalls][n_units][cap]
     float* err_out;         // optional, same shape
     size_t call_stride;
+    // plain-load staging (debug / A-B measurement; VO_LK_STAGING=ldg): plane geometry per level
+    int use_tma;
+    const uint8_t* img_base[VO_MAX_LEVELS];
+    const uint32_t* der_base[VO_MAX_LEVELS];
+    int pitch[VO_MAX_LEVELS];
+    size_t plane[VO_MAX_LEVELS];
 };
 
 size_t vo_lk_smem_bytes();
