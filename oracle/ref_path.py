@@ -43,6 +43,8 @@ class FeatureSet:
 
 
 # ------------------------------------------------------------------------------------ OpenCV calls
+# `float confidence = 0.999;` (visualOdometry.cpp:170) reaches cv::solvePnPRansac as (double)0.999f
+PNP_CONFIDENCE = float(np.float32(0.999))
 LK_ARGS = dict(winSize=(21, 21), maxLevel=3, flags=0, minEigThreshold=0.001)
 
 
@@ -220,10 +222,10 @@ def tracking_frame2frame(P_l, pts_l0, pts_l1, X, translation, backend="cv2"):
         tvec = np.asarray(translation, np.float64).reshape(3, 1).copy()
         ok, rvec, tvec, inl = cv2.solvePnPRansac(
             np.ascontiguousarray(X, np.float32).reshape(-1, 1, 3), np.ascontiguousarray(pts_l1, np.float32).reshape(-1, 1, 2),
-            K, dist, rvec, tvec, True, 500, 0.5, 0.999, None, cv2.SOLVEPNP_ITERATIVE)
+            K, dist, rvec, tvec, True, 500, 0.5, PNP_CONFIDENCE, None, cv2.SOLVEPNP_ITERATIVE)
         R, _ = cv2.Rodrigues(rvec)
         inl = np.zeros((0,), np.int32) if inl is None else inl.ravel().astype(np.int32)
         return R, tvec.ravel(), inl, rvec.ravel()
     from . import pnp_ref
-    res = pnp_ref.solve_pnp_ransac(X, pts_l1, K, np.zeros(3), translation)
+    res = pnp_ref.solve_pnp_ransac(X, pts_l1, K, np.zeros(3), translation, confidence=PNP_CONFIDENCE)
     return pnp_ref.rodrigues(res["rvec"]), res["tvec"], res["inliers"], res["rvec"]

@@ -1,0 +1,84 @@
+"""Whole-path parity (A1..A9) through the batched C-ABI on the GPU against
+the reference path: cv2 4.13.0 driven through the verbatim glue restatement (oracle/ref_path.py).
+
+Gates (BASELINE.json north_star): tracked-feature indices and RANSAC inlier lists bit-exact;
+LK positions bit-exact (stronger than the 1e-4 asked); [R|t] within 1e-4 relative.
+"""
+import numpy as np
+import pytest
+
+from visual_odom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_unit(u, n_select, t_prev, backend="cv2"):
+    """The reference's per-frame sequence with the benchmark's stride selection in place of the
+    bucketing: FAST -> select -> circularMatching -> checkValidMatch /
+    removeInvalidPoints -> triangulate -> trackingFrame2Frame."""
+    from oracle import ref_path
+    fast, _ = ref_path._backend(backend)
+    corners = fast(u["l0"])
+    pts = synth.select_features(corners, n_select)
+    fs = ref_path.FeatureSet(); fs.points = pts.copy(); fs.ages = np.zeros(len(pts), np.int32)
+    cm = ref_path.circular_matching(u["l0"], u["r0"], u["l1"], u["r1"], pts, fs, backend)
+    ok = ref_path.check_valid_match(cm["l0"], cm["l0_ret"], 0)
+    pL0, pR0, pL1, pR1 = (ref_path.remove_invalid_points(cm[k], ok) for k in ("l0", "r0", "l1", "r1"))
+    X = ref_path.triangulate(u["P_l"], u["P_r"], pL0, pR0, backend)
+    R, t, inl, rvec = ref_path.tracking_frame2frame(u["P_l"], pL0, pL1, X, t_prev, backend)
+    return dict(n_detected=len(corners), pts=pts, kept3=cm["kept_idx"], kept=cm["kept_idx"][ok], l0=pL0, r0=pR0, l1=pL1,
+                r1=pR1, X=X, R=R, t=t, inliers=inl)
+
+
+def check_unit(got_res, got, ref):
+    assert got_res["n_detected"] == ref["n_detected"]
+    assert np.array_equal(got["pts_in"], ref["pts"])
+    assert got_res["n_tracked"] == len(ref["kept3"])
+    assert np.array_equal(got["kept_idx"], ref["kept"]), "tracked-feature indices differ"
+    for k in ("l0", "r0", "l1", "r1"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(got["X"], ref["X"])
+    assert np.array_equal(got["inliers"], ref["inliers"]), "RANSAC inlier list differs"
+    assert np.linalg.norm(got_res["R"] - ref["R"]) / np.linalg.norm(ref["R"]) <= 1e-4
+    assert np.linalg.norm(got_res["tvec"] - ref["t"]) / np.linalg.norm(ref["t"]) <= 1e-4
+
+
+@pytest.mark.parametrize("w,h,n_sel,cal", [(1241, 376, 2000, "kitti"), (1920, 1080, 4000, "zed")])
+def test_whole_path_vs_cv2(ctx, w, h, n_sel, cal):
+    pytest.importorskip("cv2")
+    c = synth.KITTI00 if cal == "kitti" else synth.ZED
+    seeds = [0, 1] if cal == "kitti" else [2]
+    units = [synth.stereo_unit(w, h, s, cal=c) for s in seeds]
+    t_prev = (0.0, 0.0, -0.8)
+    ctx.batch_configure(w, h, len(units), units[0]["P_l"], units[0]["P_r"])
+    arr, keep, pitch = ctx.make_units([dict(u, n_select=n_sel, t_prev=t_prev) for u in units])
+    res = ctx.frame_batch(arr, pitch)
+    for i, u in enumerate(units):
+        ref = reference_unit(u, n_sel, np.array(t_prev))
+        got = ctx.batch_fetch(i, res[i])
+        check_unit(res[i], got, ref)
+        assert res[i]["n_valid"] > 0.25 * n_sel and res[i]["n_inliers"] > 0.3 * res[i]["n_valid"]
+        # the recovered motion is the synthetic ego-motion
+        assert np.linalg.norm(res[i]["tvec"] - u["tvec"]) < 0.05
+
+
+def test_given_features_and_batch_independence(ctx):
+    """Results of a unit do not depend on what else is in the batch (needed for sharding)."""
+    pytest.importorskip("cv2")
+    from oracle import cref
+    w, h = 640, 240
+    units = [synth.stereo_unit(w, h, s) for s in (3, 4, 5)]
+    feats = [synth.select_features(cref.fast_detect(u["l0"])[0], 500) for u in units]
+    ctx.batch_configure(w, h, 3, units[0]["P_l"], units[0]["P_r"])
+    arr, keep, pitch = ctx.make_units([dict(u, pts=f, t_prev=(0, 0, -0.8)) for u, f in zip(units, feats)])
+    res3 = ctx.frame_batch(arr, pitch)
+    got3 = [ctx.batch_fetch(i, res3[i]) for i in range(3)]
+    for i in range(3):
+        ctx.batch_configure(w, h, 1, units[0]["P_l"], units[0]["P_r"])
+        a1, k1, p1 = ctx.make_units([dict(units[i], pts=feats[i], t_prev=(0, 0, -0.8))])
+        r1 = ctx.frame_batch(a1, p1)[0]
+        g1 = ctx.batch_fetch(0, r1)
+        assert r1["n_valid"] == res3[i]["n_valid"] and r1["n_inliers"] == res3[i]["n_inliers"]
+        for k in ("kept_idx", "l0", "l1", "X", "inliers"):
+            assert np.array_equal(g1[k], got3[i][k]), k
+        assert np.array_equal(r1["rvec"], res3[i]["rvec"]) and np.array_equal(r1["tvec"], res3[i]["tvec"])

@@ -16,6 +16,7 @@ REPO = os.path.dirname(ROOT)
 CSRC = os.path.join(ROOT, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(ROOT, "libvo_b200.so")
+HOSTCHECK_LIB = os.path.join(ROOT, "libvo_hostcheck.so")
 ORACLE_DIR = os.path.join(REPO, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
@@ -69,6 +70,20 @@ def build_native(verbose=False, force=False):
     return LIB
 
 
+def build_hostcheck(force=False):
+    """pnp_math.cuh compiled for the host (g++), used by the CPU tests to check the kernels' math."""
+    src = os.path.join(CSRC, "host_check.cpp")
+    dep = [src, os.path.join(CSRC, "pnp_math.cuh")]
+    if force or _newer(dep, HOSTCHECK_LIB):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src,
+               "-o", HOSTCHECK_LIB]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("hostcheck build failed")
+    return HOSTCHECK_LIB
+
+
 def build_oracle(force=False):
     srcs = sorted(os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".c"))
     os.makedirs(os.path.dirname(ORACLE_LIB), exist_ok=True)
@@ -86,4 +101,5 @@ if __name__ == "__main__":
     v = "-v" in sys.argv
     f = "-f" in sys.argv
     print(build_native(verbose=v, force=f))
+    print(build_hostcheck(force=f))
     print(build_oracle(force=f))

@@ -233,3 +233,66 @@ class Context:
                                     _p(R), C.byref(iters))
         self._check(rc)
         return {"rvec": rvec, "tvec": tvec, "R": R.reshape(3, 3), "inliers": inl[:n_in.value], "iters": iters.value}
+
+    # ---- batched whole-path API ------------------------------------------------------------------
+    def batch_configure(self, w, h, n_units, P_l, P_r):
+        P_l = np.ascontiguousarray(P_l, np.float32).reshape(12); P_r = np.ascontiguousarray(P_r, np.float32).reshape(12)
+        self._check(self.lib.vo_batch_configure(self.h, w, h, n_units, _p(P_l), _p(P_r)))
+        self._batch_geom = (w, h, n_units)
+
+    def make_units(self, units):
+        """units: list of dicts(l0,r0,l1,r1 uint8 HxW [, pts (n,2) f32 | n_select int] [, t_prev]).
+        Returns (ctypes array, keep-alive list, pitch)."""
+        arr = (VoUnit * len(units))()
+        keep = []
+        pitch = None
+        for i, u in enumerate(units):
+            imgs = [self._img(u[k]) for k in ("l0", "r0", "l1", "r1")]
+            for a in imgs:
+                assert a.shape == (self._batch_geom[1], self._batch_geom[0])
+                pitch = pitch or a.strides[0]
+                assert a.strides[0] == pitch
+            keep.append(imgs)
+            arr[i].l0, arr[i].r0, arr[i].l1, arr[i].r1 = (a.ctypes.data for a in imgs)
+            if u.get("pts") is not None:
+                pts = np.ascontiguousarray(u["pts"], np.float32).reshape(-1, 2)
+                keep.append(pts)
+                arr[i].pts = pts.ctypes.data
+                arr[i].n_pts = len(pts)
+            else:
+                arr[i].pts = None
+                arr[i].n_pts = int(u["n_select"])
+            t = u.get("t_prev", (0.0, 0.0, 0.0))
+            for k in range(3):
+                arr[i].t_prev[k] = float(t[k])
+        return arr, keep, pitch
+
+    def batch_upload(self, arr, pitch):
+        self._check(self.lib.vo_batch_upload(self.h, arr, len(arr), pitch))
+
+    def batch_run(self):
+        self._check(self.lib.vo_batch_run(self.h))
+
+    def batch_download(self, n_units):
+        res = (VoUnitResult * n_units)()
+        self._check(self.lib.vo_batch_download(self.h, res, n_units))
+        return [self._result_dict(r) for r in res]
+
+    def frame_batch(self, arr, pitch):
+        res = (VoUnitResult * len(arr))()
+        self._check(self.lib.vo_frame_batch(self.h, arr, len(arr), pitch, res))
+        return [self._result_dict(r) for r in res]
+
+    @staticmethod
+    def _result_dict(r):
+        return dict(n_features=r.n_features, n_detected=r.n_detected, n_tracked=r.n_tracked, n_valid=r.n_valid,
+                    n_inliers=r.n_inliers, ransac_iters=r.ransac_iters, pnp_status=r.pnp_status,
+                    rvec=np.array(r.rvec[:]), tvec=np.array(r.tvec[:]), R=np.array(r.R[:]).reshape(3, 3))
+
+    def batch_fetch(self, unit, res):
+        nf, nv, ni = res["n_features"], res["n_valid"], res["n_inliers"]
+        pts_in = np.zeros((max(nf, 1), 2), np.float32); pts4 = np.zeros((4, max(nv, 1), 2), np.float32)
+        kept = np.zeros(max(nv, 1), np.int32); X = np.zeros((max(nv, 1), 3), np.float32); inl = np.zeros(max(ni, 1), np.int32)
+        self._check(self.lib.vo_batch_fetch(self.h, unit, _p(pts_in), _p(pts4), _p(kept), _p(X), _p(inl)))
+        return dict(pts_in=pts_in[:nf], l0=pts4[0, :nv], r0=pts4[1, :nv], l1=pts4[2, :nv], r1=pts4[3, :nv],
+                    kept_idx=kept[:nv], X=X[:nv], inliers=inl[:ni])

@@ -1,0 +1,150 @@
+// batch.cu -- the batched, device-resident whole-path API (vo_batch_*, vo_frame_batch).
+//
+// One call runs, for every resident work unit and with no host round trip in between:
+//   [FAST on L0 + even-stride selection]  ->  pyramids  ->  LK ring (L0->R0->R1->L1->L0)
+//   ->  status / negative-coordinate / circular filters  ->  DLT triangulation  ->  PnP/RANSAC + LM
+// i.e. reference src/visualOdometry.cpp:81-129 (matchingFeatures, with the bucketing replaced by
+// the benchmark's stride selection), src/main.cpp:170-171 and src/visualOdometry.cpp:132-193.
+#include "ctx.h"
+#include <string.h>
+
+__global__ void k_pack_counts(vo_unit_result_dev* res, const int* n_pts, const int* n_det, const int* n3, const int* n5,
+                              int n_units, int detect)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    res[u].n_features = n_pts[u];
+    res[u].n_detected = detect ? n_det[u] : 0;
+    res[u].n_tracked = n3[u];
+    res[u].n_valid = n5[u];
+}
+
+extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const float P_l[12], const float P_r[12])
+{
+    if (!ctx) return VO_E_INVALID;
+    if (!P_l || !P_r || n_units <= 0) { vo_set_error(ctx, "bad argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int rc = vo_ensure_state(ctx, w, h, n_units, 4);
+    if (rc) return rc;
+    memcpy(ctx->P_l, P_l, 12 * sizeof(float));
+    memcpy(ctx->P_r, P_r, 12 * sizeof(float));
+    ctx->have_P = true;
+    ctx->batch_units = n_units;
+    ctx->batch_uploaded = 0;
+    return VO_OK;
+}
+
+extern "C" int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch)
+{
+    if (!ctx || !units) return VO_E_INVALID;
+    if (n_units <= 0 || n_units > ctx->batch_units) { vo_set_error(ctx, "n_units=%d outside the configured batch (%d)", n_units, ctx->batch_units); return VO_E_INVALID; }
+    if (pitch < (size_t)ctx->w) { vo_set_error(ctx, "pitch %zu < width %d", pitch, ctx->w); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int w = ctx->w, h = ctx->h, cap = ctx->cap;
+    // small per-unit scalars go through one pinned staging block
+    const size_t stage_bytes = (size_t)n_units * (2 * sizeof(int) + 3 * sizeof(double));
+    int rc = vo_ensure_pinned(ctx, stage_bytes + 64);
+    if (rc) return rc;
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // staging block may still be in flight
+    double* h_tprev = (double*)ctx->h_pinned;
+    int* h_npts = (int*)(h_tprev + 3 * (size_t)n_units);
+    int* h_want = h_npts + n_units;
+    bool detect = (units[0].pts == nullptr);
+    int max_pts = 0;
+    for (int u = 0; u < n_units; u++) {
+        const vo_unit& U = units[u];
+        if (!U.l0 || !U.r0 || !U.l1 || !U.r1) { vo_set_error(ctx, "unit %d: null image", u); return VO_E_INVALID; }
+        if ((U.pts == nullptr) != detect) { vo_set_error(ctx, "units must all carry features or all request detection"); return VO_E_INVALID; }
+        if (U.n_pts < 0 || U.n_pts > cap) { vo_set_error(ctx, "unit %d: n_pts=%d outside [0,%d]", u, U.n_pts, cap); return VO_E_CAPACITY; }
+        const uint8_t* imgs[4] = {U.l0, U.r0, U.l1, U.r1};
+        for (int k = 0; k < 4; k++)
+            VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_raw + ((size_t)u * 4 + k) * w * h, w, imgs[k], pitch, w, h,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+        if (!detect && U.n_pts > 0)
+            VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in + (size_t)u * cap, U.pts, (size_t)U.n_pts * sizeof(float2),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        h_npts[u] = U.n_pts; h_want[u] = U.n_pts;
+        for (int k = 0; k < 3; k++) h_tprev[3 * u + k] = U.t_prev[k];
+        if (U.n_pts > max_pts) max_pts = U.n_pts;
+    }
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tprev, h_tprev, (size_t)n_units * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(detect ? ctx->d_want : ctx->d_npts, detect ? h_want : h_npts, (size_t)n_units * sizeof(int),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    ctx->batch_uploaded = n_units;
+    ctx->batch_detect = detect;
+    ctx->batch_max_pts = max_pts;
+    return VO_OK;
+}
+
+extern "C" int vo_batch_run(vo_ctx* ctx)
+{
+    if (!ctx) return VO_E_INVALID;
+    const int units = ctx->batch_uploaded;
+    if (units <= 0) { vo_set_error(ctx, "vo_batch_run: nothing uploaded"); return VO_E_INVALID; }
+    if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_run: projection matrices not set"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    ctx->imgs_per_unit = 4;
+    int rc;
+    if (ctx->batch_detect) {
+        if ((rc = vo_run_fast(ctx, units, 0, false))) return rc;
+        ctx->launches += vo_launch_select(ctx->d_corners, ctx->corner_cap, ctx->d_ndet, ctx->d_want, ctx->d_pts_in, ctx->cap,
+                                          ctx->d_npts, units, ctx->stream);
+    }
+    const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};
+    if ((rc = vo_run_lk(ctx, units, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, units, false))) return rc;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    if ((rc = vo_run_triangulate(ctx, units, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
+    if ((rc = vo_run_pnp(ctx, units, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
+    k_pack_counts<<<(units + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_results, ctx->d_npts, ctx->d_ndet, ctx->d_n3, ctx->d_n5, units,
+                                                             ctx->batch_detect ? 1 : 0);
+    ctx->launches += 1;
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+extern "C" int vo_batch_download(vo_ctx* ctx, vo_unit_result* results, int n_units)
+{
+    if (!ctx || !results) return VO_E_INVALID;
+    if (n_units <= 0 || n_units > ctx->batch_uploaded) { vo_set_error(ctx, "n_units=%d outside the resident batch (%d)", n_units, ctx->batch_uploaded); return VO_E_INVALID; }
+    static_assert(sizeof(vo_unit_result) == sizeof(vo_unit_result_dev), "result record layout");
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    VO_CUDA_CHECK(cudaMemcpyAsync(results, ctx->d_results, (size_t)n_units * sizeof(vo_unit_result), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch, vo_unit_result* results)
+{
+    int rc = vo_batch_upload(ctx, units, n_units, pitch);
+    if (rc) return rc;
+    if ((rc = vo_batch_run(ctx))) return rc;
+    return vo_batch_download(ctx, results, n_units);
+}
+
+extern "C" int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,
+                              vo_point3f* X, int32_t* inliers)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (unit < 0 || unit >= ctx->batch_uploaded) { vo_set_error(ctx, "unit %d outside the resident batch", unit); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    vo_unit_result_dev r;
+    VO_CUDA_CHECK(cudaMemcpyAsync(&r, ctx->d_results + unit, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const size_t cs = (size_t)ctx->units * ctx->cap, ub = (size_t)unit * ctx->cap;
+    if (pts_in && r.n_features > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(pts_in, ctx->d_pts_in + ub, (size_t)r.n_features * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pts4 && r.n_valid > 0)
+        for (int k = 0; k < 4; k++)
+            VO_CUDA_CHECK(cudaMemcpyAsync(pts4 + (size_t)k * r.n_valid, ctx->d_valid4 + k * cs + ub, (size_t)r.n_valid * sizeof(float2),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    if (kept_idx && r.n_valid > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(kept_idx, ctx->d_idx5 + ub, (size_t)r.n_valid * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (X && r.n_valid > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(X, ctx->d_X + ub, (size_t)r.n_valid * sizeof(float3), cudaMemcpyDeviceToHost, ctx->stream));
+    if (inliers && r.n_inliers > 0)
+        VO_CUDA_CHECK(cudaMemcpyAsync(inliers, ctx->d_inliers + ub, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}

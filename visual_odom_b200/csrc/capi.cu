@@ -92,3 +92,96 @@ extern "C" int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* 
     if (n_kept) *n_kept = n3;
     return VO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_any_state(vo_ctx* ctx)
+{
+    if (ctx->units > 0) return VO_OK;
+    return vo_ensure_state(ctx, 64, 64, 1, 4);
+}
+
+extern "C" int vo_fast_detect(vo_ctx* ctx, const uint8_t* img, int w, int h, size_t pitch, vo_point2f* out,
+                              float* response, int cap, int* n_out)
+{
+    int rc = check_common(ctx, w, h, pitch, 0);
+    if (rc) return rc;
+    if (!img || !n_out || (cap > 0 && !out)) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = vo_ensure_state(ctx, w, h, 1, 4))) return rc;
+    ctx->imgs_per_unit = 4;
+    if ((rc = upload_image(ctx, 0, img, w, h, pitch))) return rc;
+    if ((rc = vo_run_fast(ctx, 1, 0, response != nullptr))) return rc;
+    int n = 0;
+    VO_CUDA_CHECK(cudaMemcpyAsync(&n, ctx->d_ndet, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    int m = n < cap ? n : cap;
+    if (m > ctx->corner_cap) m = ctx->corner_cap;
+    if (m > 0) {
+        VO_CUDA_CHECK(cudaMemcpyAsync(out, ctx->d_corners, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        if (response) VO_CUDA_CHECK(cudaMemcpyAsync(response, ctx->d_resp, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n > m) { vo_set_error(ctx, "%d corners found, %d returned (capacity)", n, m); return VO_E_CAPACITY; }
+    return VO_OK;
+}
+
+extern "C" int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[12], const vo_point2f* pts_l,
+                              const vo_point2f* pts_r, int n, vo_point3f* X)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (n < 0 || !P_l || !P_r) { vo_set_error(ctx, "bad argument"); return VO_E_INVALID; }
+    if (n == 0) return VO_OK;
+    if (n > ctx->cap) { vo_set_error(ctx, "n=%d exceeds max_features=%d", n, ctx->cap); return VO_E_CAPACITY; }
+    if (!pts_l || !pts_r || !X) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int rc = ensure_any_state(ctx);
+    if (rc) return rc;
+    memcpy(ctx->P_l, P_l, 12 * sizeof(float)); memcpy(ctx->P_r, P_r, 12 * sizeof(float)); ctx->have_P = true;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4, pts_l, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4 + cs, pts_r, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n5, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vo_run_triangulate(ctx, 1, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    VO_CUDA_CHECK(cudaMemcpyAsync(X, ctx->d_X, (size_t)n * sizeof(float3), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
+
+extern "C" int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f* x, int n, const float K[9],
+                             double rvec_io[3], double tvec_io[3], int32_t* inliers, int* n_inliers,
+                             double R_out[9], int* ransac_iters)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (n_inliers) *n_inliers = 0;
+    if (n < 0 || !K || !rvec_io || !tvec_io) { vo_set_error(ctx, "bad argument"); return VO_E_INVALID; }
+    if (n < 4) { vo_set_error(ctx, "solvePnPRansac needs >= 4 points (got %d); the reference aborts here", n); return VO_E_TOO_FEW_POINTS; }
+    if (n == 4) { vo_set_error(ctx, "n == 4 selects OpenCV's P3P RANSAC kernel, which this library does not build"); return VO_E_UNSUPPORTED; }
+    if (n > ctx->cap) { vo_set_error(ctx, "n=%d exceeds max_features=%d", n, ctx->cap); return VO_E_CAPACITY; }
+    if (!X || !x) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
+    if (rvec_io[0] != 0 || rvec_io[1] != 0 || rvec_io[2] != 0) {
+        vo_set_error(ctx, "non-zero initial rvec is not supported (the reference resets rvec to 0 every call, visualOdometry.cpp:162)");
+        return VO_E_UNSUPPORTED;
+    }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int rc = ensure_any_state(ctx);
+    if (rc) return rc;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_X, X, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4 + 2 * cs, x, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n5, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tprev, tvec_io, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vo_run_pnp(ctx, 1, ctx->d_valid4 + 2 * cs, ctx->d_n5, K))) return rc;
+    vo_unit_result_dev r;
+    VO_CUDA_CHECK(cudaMemcpyAsync(&r, ctx->d_results, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; k++) { rvec_io[k] = r.rvec[k]; tvec_io[k] = r.tvec[k]; }
+    if (R_out) for (int k = 0; k < 9; k++) R_out[k] = r.R[k];
+    if (ransac_iters) *ransac_iters = r.ransac_iters;
+    if (n_inliers) *n_inliers = r.n_inliers;
+    if (inliers && r.n_inliers > 0) {
+        VO_CUDA_CHECK(cudaMemcpyAsync(inliers, ctx->d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    return VO_OK;
+}

@@ -24,7 +24,7 @@ extern "C" void vo_default_params(vo_params* p)
     p->circ_threshold = 0;
     p->pnp_iterations = 500;
     p->pnp_reproj_error = 0.5f;
-    p->pnp_confidence = 0.999;
+    p->pnp_confidence = (double)0.999f;   // the reference stores it in a float (visualOdometry.cpp:170)
     p->max_features = 8192;
     p->max_units = 1;
 }
@@ -243,6 +243,28 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_valid4, 4 * uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_idx5, uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_n5, (size_t)units));
+    // FAST
+    ctx->corner_cap = (w * h) / 8 > 65536 ? (w * h) / 8 : 65536;
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_score, (size_t)units * w * h));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_rowbuf, (size_t)units * h * w));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_rowcount, (size_t)units * h));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_rowoff, (size_t)units * h));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_ndet, (size_t)units));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_corners, (size_t)units * ctx->corner_cap));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_resp, (size_t)units * ctx->corner_cap));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_want, (size_t)units));
+    // triangulation + PnP
+    const size_t its = (size_t)ctx->p.pnp_iterations;
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_X, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_tprev, (size_t)units * 3));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_pnp_state, (size_t)units));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_subsets, (size_t)units * its * 5));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_models, (size_t)units * its * 12));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_counts, (size_t)units * its));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_inliers, uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_results, (size_t)units));
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_results, 0, (size_t)units * sizeof(vo_unit_result_dev), ctx->stream));
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, (size_t)units * 3 * sizeof(double), ctx->stream));
     ctx->w = w; ctx->h = h; ctx->units = units;
     int rc = encode_maps(ctx);
     if (rc != VO_OK) { vo_free_state(ctx); return rc; }
@@ -323,5 +345,53 @@ int vo_run_filter(vo_ctx* ctx, int units, bool with_ages)
     f.n5 = ctx->d_n5;
     VO_CUDA_CHECK(vo_launch_ring_filter(f, units, ctx->stream));
     ctx->launches += 1;
+    return VO_OK;
+}
+
+
+int vo_run_fast(vo_ctx* ctx, int units, int plane_in_unit, bool want_resp)
+{
+    FastArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_units = units;
+    a.img_tab = ctx->d_raw_tab + plane_in_unit;
+    a.img_stride_idx = ctx->imgs_per_unit;
+    a.w = ctx->w; a.h = ctx->h; a.pitch = ctx->w;
+    a.threshold = ctx->p.fast_threshold; a.nonmax = ctx->p.fast_nonmax;
+    a.score = ctx->d_score; a.score_plane = (size_t)ctx->w * ctx->h;
+    a.rowbuf = ctx->d_rowbuf; a.rowcap = ctx->w;
+    a.rowcount = ctx->d_rowcount; a.rowoff = ctx->d_rowoff; a.n_det = ctx->d_ndet;
+    a.corners = ctx->d_corners; a.resp = want_resp ? ctx->d_resp : nullptr; a.corner_cap = ctx->corner_cap;
+    ctx->launches += vo_launch_fast(a, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+int vo_run_triangulate(vo_ctx* ctx, int units, const float2* pts_l, const float2* pts_r, const int* n)
+{
+    TriArgs t;
+    memset(&t, 0, sizeof(t));
+    t.cap = ctx->cap; t.n_pts = n; t.pts_l = pts_l; t.pts_r = pts_r; t.X = ctx->d_X;
+    for (int k = 0; k < 12; k++) { t.Pl[k] = (double)ctx->P_l[k]; t.Pr[k] = (double)ctx->P_r[k]; }
+    ctx->launches += vo_launch_triangulate(t, units, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+int vo_run_pnp(vo_ctx* ctx, int units, const float2* pts2d, const int* n, const float* K9)
+{
+    PnpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_units = units; a.cap = ctx->cap; a.iterations = ctx->p.pnp_iterations;
+    a.n_pts = n; a.X = ctx->d_X; a.x = pts2d;
+    a.fu = (double)K9[0]; a.fv = (double)K9[4]; a.uc = (double)K9[2]; a.vc = (double)K9[5];
+    const double thr = (double)ctx->p.pnp_reproj_error;      // float -> double, squared in double, stored float
+    a.thr2 = (float)(thr * thr);
+    a.confidence = ctx->p.pnp_confidence;
+    a.t_prev = ctx->d_tprev;
+    a.state = ctx->d_pnp_state; a.subsets = ctx->d_subsets; a.models = ctx->d_models; a.counts = ctx->d_counts;
+    a.inliers = ctx->d_inliers; a.results = ctx->d_results;
+    ctx->launches += vo_launch_pnp(a, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "lk_ring.h"
 #include "filter.h"
+#include "fast.h"
+#include "pnp.h"
 #include "../../include/vo_b200.h"
 #include <vector>
 #include <stdarg.h>
@@ -41,6 +43,25 @@ struct vo_ctx {
     float2* d_valid4 = nullptr;         // [4][units][cap]
     int* d_idx5 = nullptr;              // [units][cap]
     int* d_n5 = nullptr;                // [units]
+    // FAST
+    uint8_t* d_score = nullptr;         // [units][h*w]
+    uint16_t* d_rowbuf = nullptr;       // [units][h][w]
+    int* d_rowcount = nullptr;          // [units][h]
+    int* d_rowoff = nullptr;            // [units][h]
+    int* d_ndet = nullptr;              // [units]
+    float2* d_corners = nullptr;        // [units][corner_cap]
+    float* d_resp = nullptr;            // [units][corner_cap]
+    int* d_want = nullptr;              // [units] features to select (batched path)
+    int corner_cap = 0;
+    // triangulation + PnP
+    float3* d_X = nullptr;              // [units][cap]
+    double* d_tprev = nullptr;          // [units][3]
+    PnpState* d_pnp_state = nullptr;    // [units]
+    int* d_subsets = nullptr;           // [units][iters][5]
+    double* d_models = nullptr;         // [units][iters][12]
+    int* d_counts = nullptr;            // [units][iters]
+    int* d_inliers = nullptr;           // [units][cap]
+    vo_unit_result_dev* d_results = nullptr;   // [units]
     std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
 
     // ---- pinned host staging ------------------------------------------------------------------
@@ -54,6 +75,12 @@ struct vo_ctx {
     long long lk_n = 0;
     bool lk_timing = true;
     bool lk_use_tma = true;
+
+    // ---- batched path bookkeeping -----------------------------------------------------------
+    int batch_units = 0;            // units configured by vo_batch_configure
+    int batch_uploaded = 0;         // units currently resident
+    bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
+    int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
 };
 
 void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
@@ -63,3 +90,8 @@ int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 // run pyramids + LK (ncalls chained) for `units` units; images must already be in d_raw/d_raw_tab
 int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int* img_next, bool want_err);
 int vo_run_filter(vo_ctx* ctx, int units, bool with_ages);
+// FAST on raw plane `plane_in_unit` of each unit -> d_corners / d_ndet
+int vo_run_fast(vo_ctx* ctx, int units, int plane_in_unit, bool want_resp);
+// triangulate pts_l/pts_r ([units][cap], counts n) -> d_X ; PnP on (d_X, pts2d) -> d_results / d_inliers
+int vo_run_triangulate(vo_ctx* ctx, int units, const float2* pts_l, const float2* pts_r, const int* n);
+int vo_run_pnp(vo_ctx* ctx, int units, const float2* pts2d, const int* n, const float* K9);
