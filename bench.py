@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/sec of the circularMatching() hot path on B200 (+ the CPU reference arm).
+
+  python bench.py --gpus N --steps K --warmup W            this library (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's OpenCV CPU path on the host cores
+
+One "step" = one pass of the whole path (FAST -> select 2000 -> pyramids -> LK ring -> filters ->
+triangulation -> PnP/RANSAC) over `--units` independent KITTI-shaped synthetic stereo pairs per GPU.
+Prints ONE JSON line (see README "bench contract"):
+  value      frames/s, inputs resident in HBM when the timed region starts (vo_batch_run only)
+  e2e        frames/s through the C-ABI with pinned HOST buffers: H2D of the 4 images per unit +
+             run + D2H of the result records inside the timed region (vo_frame_batch)
+  roofline   LK ring kernel: algorithmic bytes (17044 B per feature-ring) / its own
+             CUDA-event time on the launching stream, vs the measured HBM copy bandwidth
+  cpu_baseline  cv2 (the OpenCV the reference links) through the reference glue, timed on this host
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG, N_FEAT = 1241, 376, 2000
+LK_BYTES_PER_FEATURE = 4 * (4 * ((21 + 3) ** 2 + (21 + 1) ** 2) + 21)      # 17044, SURVEY.md 8(d)
+METRIC = "stereo frames/sec at 1241x376, 2000 feats; LK kernel HBM GB/s vs roofline"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--units", type=int, default=8, help="independent stereo pairs per step per GPU")
+    ap.add_argument("--features", type=int, default=N_FEAT)
+    ap.add_argument("--cpu-sample", type=int, default=12, help="frames timed for cpu_baseline")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_frames(units, n_feat, frames, threads=None):
+    """Times the reference's CPU path (cv2 through oracle/ref_path.py glue) on `frames` frames."""
+    import cv2
+    from oracle import ref_path
+    from visual_odom_b200 import synth
+    if threads is not None:
+        cv2.setNumThreads(threads)
+    t_prev = np.array([0.0, 0.0, -0.8])
+
+    def one(u):
+        corners = ref_path.fast_cv2(u["l0"])
+        pts = synth.select_features(corners, n_feat)
+        fs = ref_path.FeatureSet(); fs.points = pts; fs.ages = np.zeros(len(pts), np.int32)
+        cm = ref_path.circular_matching(u["l0"], u["r0"], u["l1"], u["r1"], pts, fs, "cv2")
+        ok = ref_path.check_valid_match(cm["l0"], cm["l0_ret"], 0)
+        pL0, pR0, pL1 = (ref_path.remove_invalid_points(cm[k], ok) for k in ("l0", "r0", "l1"))
+        X = ref_path.triangulate(u["P_l"], u["P_r"], pL0, pR0, "cv2")
+        return ref_path.tracking_frame2frame(u["P_l"], pL0, pL1, X, t_prev, "cv2")
+
+    for i in range(min(3, len(units))):
+        one(units[i])                      # warm-up
+    t0 = time.perf_counter()
+    for i in range(frames):
+        one(units[i % len(units)])
+    dt = time.perf_counter() - t0
+    return frames / dt, dt, cv2.getNumThreads()
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own OpenCV CPU implementation on the host cores."""
+    if rank != 0:
+        return
+    from visual_odom_b200 import synth
+    units = [synth.stereo_unit(W_IMG, H_IMG, s) for s in range(args.units)]
+    # each step = args.units frames on the CPU (bounded: steps+warmup passes over the same units)
+    for _ in range(args.warmup):
+        cpu_reference_frames(units, args.features, len(units))
+    t_total = 0.0
+    cores = 0
+    for _ in range(args.steps):
+        fps, dt, cores = cpu_reference_frames(units, args.features, len(units))
+        t_total += dt
+    value = args.steps * len(units) / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/i32 fixed point + f32 (LK), f64 (pose)", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps}x{len(units)} frames; cv2 {__import__('cv2').__version__} (the OpenCV build the "
+                                   "reference's calls resolve to) through the oracle/ref_path.py glue restatement; "
+                                   f"os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"KITTI-00 shaped synthetic stereo {W_IMG}x{H_IMG}, {args.features} FAST features (thr 20, even-stride "
+                        f"selection), LK 21x21 maxLevel=3 (4 images) 30 it / 0.01, PnP RANSAC 500/0.5/0.999; "
+                        f"{args.units} independent stereo pairs per step per GPU",
+            "units_per_gpu": args.units, "global_units": args.units * world, "features": args.features,
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"units sharded over {world} GPU(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from visual_odom_b200 import synth
+    from visual_odom_b200.capi import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this library has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.units
+    # work-queue scatter: rank 0 owns the unit table (seeds), broadcast over NCCL
+    table = torch.arange(world * B, dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.broadcast(table, src=0)
+    seeds = table[rank * B:(rank + 1) * B].cpu().tolist()
+    units = [synth.stereo_unit(W_IMG, H_IMG, s) for s in seeds]
+
+    # pinned host copies of the images (what a capture / decode thread would hand over)
+    pinned = []
+    for u in units:
+        d = {}
+        for k in ("l0", "r0", "l1", "r1"):
+            t = torch.empty((H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
+            t.numpy()[:] = u[k]
+            d[k] = t.numpy()
+        pinned.append(d)
+    keep_alive = pinned
+
+    ctx = Context(local_rank, max_features=max(2048, args.features), max_units=B)
+    # a real (non-default) stream shared by torch's events and the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.batch_configure(W_IMG, H_IMG, B, units[0]["P_l"], units[0]["P_r"])
+    arr, keep, pitch = ctx.make_units([dict(p, n_select=args.features, t_prev=(0.0, 0.0, -0.8)) for p in pinned])
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-input throughput (`value`) ----------------
+    ctx.batch_upload(arr, pitch)
+    for _ in range(args.warmup):
+        ctx.batch_run()
+    torch.cuda.synchronize()
+    ctx.lk_kernel_time(reset=True)
+    launches0 = ctx.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                 # L2 flush, outside the timed events
+        ev[s][0].record(stream)
+        ctx.batch_run()
+        ev[s][1].record(stream)
+    barrier()
+    t_dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.kernel_launches() - launches0
+    lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
+    res = ctx.batch_download(B)
+    feats_per_launch = sum(r["n_features"] for r in res)
+
+    # ---------------- end-to-end through the C-ABI with host buffers (`e2e`) ----------------
+    for _ in range(max(1, args.warmup)):
+        ctx.frame_batch(arr, pitch)
+    gathered = None
+    barrier()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        e2e_ev[s][0].record(stream)
+        res_e2e = ctx.frame_batch(arr, pitch)          # H2D + run + D2H, synchronous at return
+        if world > 1:                                    # result gather: fixed-size records over NCCL
+            rec = torch.tensor([[r["n_valid"], r["n_inliers"]] for r in res_e2e], dtype=torch.int32, device="cuda")
+            gathered = [torch.empty_like(rec) for _ in range(world)]
+            dist.all_gather(gathered, rec)
+        e2e_ev[s][1].record(stream)
+    barrier()
+    t_e2e_wall = time.perf_counter() - t_wall0
+    t_e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_ev)
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks (device-timed)
+    tt = torch.tensor([t_dev_ms, t_e2e_ms, lk_ms, float(feats_per_launch)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax = tt; tsum = tt
+    t_dev_ms, t_e2e_ms = float(tmax[0]), float(tmax[1])
+
+    if rank == 0:
+        frames = world * B * args.steps
+        value = frames / (t_dev_ms * 1e-3)
+        e2e_value = frames / (t_e2e_ms * 1e-3)
+        peak, peak_src = peaks()
+        lk_avg_ms = lk_ms / max(lk_n, 1)
+        alg_bytes = LK_BYTES_PER_FEATURE * feats_per_launch
+        achieved = alg_bytes / (lk_avg_ms * 1e-3) / 1e9 if lk_avg_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "lk_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu_fps, cpu_dt, cores = cpu_reference_frames(units, args.features, args.cpu_sample)
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/i32 fixed point + f32 (LK), f64 (pose)", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * 4 * W_IMG * H_IMG + B * 32,
+                    "d2h_bytes_per_step": B * 152, "ms_per_step": t_e2e_ms / args.steps,
+                    "wall_ms_per_step": 1e3 * t_e2e_wall / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_lk_ring", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "features_per_launch": feats_per_launch,
+                         "avg_launch_ms": lk_avg_ms, "lk_share_of_step": lk_ms / t_dev_ms if t_dev_ms else None,
+                         "note": "algorithmic bytes per SURVEY.md 8(d); the kernel is ALU/latency bound, see DESIGN.md"},
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.cpu_sample} frames of the same workload in {cpu_dt:.1f} s; cv2 (the OpenCV the "
+                                       f"reference's calls resolve to) through oracle/ref_path.py glue; os.cpu_count()={os.cpu_count()}"},
+            "clocks": clocks,
+            "parity": {"n_valid": [r["n_valid"] for r in res], "n_inliers": [r["n_inliers"] for r in res]},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

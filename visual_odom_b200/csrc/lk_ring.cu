@@ -81,10 +81,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 #define DW 28                   // row pitch (uint32) of the derivative box
 #define I_ROWS 22
 #define J_ROWS 32
+#define CHQ 448                 // floats per quantity in the chain buffer
 struct __align__(128) WarpSmem {
     uint8_t iwin[IW * I_ROWS + 96];     // previous-image window (box 48 x 22)      1056 -> 1152
     uint8_t jtile[IW * J_ROWS];         // next-image tile       (box 48 x 32)      1536
     uint32_t dwin[DW * I_ROWS + 24];    // derivative window     (box 28 x 22 u32)  2464 -> 2560
+    float chain[3 * CHQ];               // chain-ordered float addends (faithful summation)  5376
     uint64_t bar;                       // mbarrier for TMA completion
     uint64_t pad_[15];
 };
@@ -129,29 +131,34 @@ __device__ __forceinline__ int group_sum(int v, int sub, int gsize)
     return v;
 }
 
-// faithful float chain: every lane holds `cnt` addends v[0..cnt) of its chain segment;
-// returns the chain total in the LAST lane of each group (sub == gsize-1).
-template <int NV>
-__device__ __forceinline__ float chain_sum(const float (&v)[NV], int cnt, int sub)
+// Faithful float chains.  The addends of every chain lie contiguously (in chain order, zero padded
+// to a multiple of 4) in shared memory; one RUNNER lane per (quantity, chain) adds them strictly
+// in order with 128-bit loads.  5 chains x NQ quantities run concurrently on 5*NQ lanes.
+//   base  : this lane's chain start (floats), nvec : float4 count (0 for non-runner lanes)
+__device__ __forceinline__ float run_chain(const float* buf, int base, int nvec)
 {
     float acc = 0.f;
-#pragma unroll 1
-    for (int r = 0; r < 8; r++) {
-        float up = __shfl_up_sync(FULL, acc, 1);
-        if (sub == r) {
-            acc = (r == 0) ? 0.f : up;
-#pragma unroll
-            for (int k = 0; k < NV; k++)
-                if (k < cnt) acc = __fadd_rn(acc, v[k]);
-        }
+    const float4* p = reinterpret_cast<const float4*>(buf + base);
+#pragma unroll 4
+    for (int v = 0; v < nvec; v++) {
+        const float4 t = p[v];
+        acc = __fadd_rn(acc, t.x); acc = __fadd_rn(acc, t.y); acc = __fadd_rn(acc, t.z); acc = __fadd_rn(acc, t.w);
     }
     return acc;
+}
+// total of quantity q from the runner lanes 5q..5q+4:  tail + ((c0 + c2) + (c1 + c3))
+__device__ __forceinline__ float combine_chains(float acc, int q)
+{
+    const float c0 = __shfl_sync(FULL, acc, 5 * q), c1 = __shfl_sync(FULL, acc, 5 * q + 1),
+                c2 = __shfl_sync(FULL, acc, 5 * q + 2), c3 = __shfl_sync(FULL, acc, 5 * q + 3),
+                t = __shfl_sync(FULL, acc, 5 * q + 4);
+    return __fadd_rn(t, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
 }
 
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(LK_WARPS_PER_CTA * 32, LK_MIN_CTAS_PER_SM)
 k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -166,24 +173,28 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     const int npts = args.n_pts ? args.n_pts[unit] : args.cap;
     if (f >= npts) return;
 
-    // static lane -> chain-element assignment
+    // static lane -> chain-element assignment: lanes 0..23 = 4 SIMD chains x 6 lanes, 24..31 = tail
     const bool tail = lane >= 24;
     const int chain = tail ? 4 : lane / 6;
     const int sub = tail ? lane - 24 : lane - chain * 6;
     const int gsize = tail ? 8 : 6;
     const int e0 = sub * 14;                       // first chain element of this lane
     const int nel = tail ? (105 - e0 < 14 ? 105 - e0 : 14) : 14;   // elements owned (tail last lane: 7)
-    // element k -> (row, col) in the 21x21 window; pre-compute box offsets
-    int woff[14], doff[14];
+    int woff[14];                                  // element k -> offset (row*IW + col) in a u8 box
 #pragma unroll
     for (int k = 0; k < 14; k++) {
         int e = e0 + k, row, col;
         if (tail) { row = e / 5; col = 16 + e - row * 5; }
         else { row = e >> 2; col = chain + 4 * (e & 3); }
         if (k >= nel) { row = 0; col = 0; }
-        woff[k] = row * IW + col;        // offset in a 48-byte-pitch u8 box
-        doff[k] = row * DW + col;        // offset in the derivative box
+        woff[k] = row * IW + col;
     }
+    // chain-buffer slots: where this lane writes its addends, and (runner lanes) what it sums
+    const int a_slot = (tail ? 336 : chain * 84) + sub * 14;     // setup: 14 floats per lane and quantity
+    const int b_slot = tail ? 192 + sub * 14 : chain * 48 + sub * 8;   // iteration: 7 pairs (+1 zero) / 14 singles
+    const int rq = lane / 5, rc = lane - rq * 5;                 // runner: quantity, chain
+    const int a_base = rq * CHQ + (rc < 4 ? rc * 84 : 336), a_nvec = lane < 15 ? (rc < 4 ? 21 : 28) : 0;
+    const int b_base = rq * CHQ + (rc < 4 ? rc * 48 : 192), b_nvec = lane < 10 ? (rc < 4 ? 12 : 28) : 0;
 
     if (lane == 0) {
         mbar_init(&sm.bar, 1);
@@ -249,42 +260,35 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
             if (args.use_tma) { mbar_wait(&sm.bar, phase); phase ^= 1; }
 
             // ---- patch extraction: I (x32), Ix, Iy for the 14 owned elements ------------------
-            short Iv[14];
-            int dxy[14];          // lo16 = Ix, hi16 = Iy (as packed shorts)
+            int Ipk[7];           // two int16 patch intensities per register
+            int dxy[14];          // lo16 = Ix, hi16 = Iy
             float A11, A12, A22;
             {
-                float f11[14], f12[14], f22[14];
 #pragma unroll
                 for (int k = 0; k < 14; k++) {
                     const uint8_t* s0 = ib + woff[k];
-                    int ival = (s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
-                    const uint32_t* d0 = db + doff[k];
-                    uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[DW], d11 = d0[DW + 1];
+                    const int ival = (s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
+                    const int row = woff[k] / IW, col = woff[k] - row * IW;
+                    const uint32_t* d0 = db + row * DW + col;
+                    const uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[DW], d11 = d0[DW + 1];
                     int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
                               (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
                     int iy = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 +
                               ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    Iv[k] = (short)ival;
+                    if (k >= nel) { ix = 0; iy = 0; }
+                    if (k & 1) Ipk[k >> 1] |= ival << 16; else Ipk[k >> 1] = ival & 0xffff;
                     dxy[k] = (ix & 0xffff) | (iy << 16);
-                    float fx = (float)ix, fy = (float)iy;
-                    f11[k] = __fmul_rn(fx, fx); f12[k] = __fmul_rn(fx, fy); f22[k] = __fmul_rn(fy, fy);
+                    const float fx = (float)ix, fy = (float)iy;
+                    // chain-ordered addends of A11 / A12 / A22 (zero for the unused tail slots)
+                    sm.chain[0 * CHQ + a_slot + k] = __fmul_rn(fx, fx);
+                    sm.chain[1 * CHQ + a_slot + k] = __fmul_rn(fx, fy);
+                    sm.chain[2 * CHQ + a_slot + k] = __fmul_rn(fy, fy);
                 }
-                // faithful chains (A sums pass 2^24 for any corner-like texture, so no fast path here)
-                float c11 = chain_sum(f11, nel, sub);
-                float c12 = chain_sum(f12, nel, sub);
-                float c22 = chain_sum(f22, nel, sub);
-                // chain totals live in lanes 5, 11, 17, 23 (SIMD lanes 0..3) and 31 (tail)
-                float q0, q1, q2, q3, t;
-                q0 = __shfl_sync(FULL, c11, 5); q1 = __shfl_sync(FULL, c11, 11); q2 = __shfl_sync(FULL, c11, 17);
-                q3 = __shfl_sync(FULL, c11, 23); t = __shfl_sync(FULL, c11, 31);
-                float iA11 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
-                q0 = __shfl_sync(FULL, c12, 5); q1 = __shfl_sync(FULL, c12, 11); q2 = __shfl_sync(FULL, c12, 17);
-                q3 = __shfl_sync(FULL, c12, 23); t = __shfl_sync(FULL, c12, 31);
-                float iA12 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
-                q0 = __shfl_sync(FULL, c22, 5); q1 = __shfl_sync(FULL, c22, 11); q2 = __shfl_sync(FULL, c22, 17);
-                q3 = __shfl_sync(FULL, c22, 23); t = __shfl_sync(FULL, c22, 31);
-                float iA22 = __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+                __syncwarp();
+                const float acc = run_chain(sm.chain, a_base, a_nvec);
+                const float iA11 = combine_chains(acc, 0), iA12 = combine_chains(acc, 1), iA22 = combine_chains(acc, 2);
                 A11 = __fmul_rn(iA11, FLT_SCALE); A12 = __fmul_rn(iA12, FLT_SCALE); A22 = __fmul_rn(iA22, FLT_SCALE);
+                __syncwarp();
             }
             float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
             {
@@ -327,63 +331,65 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 a = npx - (float)inx; b = npy - (float)iny;
                 bilinear_weights(a, b, w00, w01, w10, w11);
                 const uint8_t* jb = sm.jtile + ry * IW + rx;
-                int pxv[14], pyv[14];
+                int dpk[7];                       // two int16 residuals per register
                 int sx = 0, sy = 0;
                 unsigned ax = 0, ay = 0;
 #pragma unroll
                 for (int k = 0; k < 14; k++) {
                     const uint8_t* s0 = jb + woff[k];
-                    int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
-                    if (k >= nel) diff = 0;
-                    int vx = diff * (int)(short)(dxy[k] & 0xffff);
-                    int vy = diff * (dxy[k] >> 16);
-                    pxv[k] = vx; pyv[k] = vy;
+                    const int Iv = (k & 1) ? (Ipk[k >> 1] >> 16) : (int)(short)(Ipk[k >> 1] & 0xffff);
+                    const int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
+                    if (k & 1) dpk[k >> 1] |= diff << 16; else dpk[k >> 1] = diff & 0xffff;
+                    const int vx = diff * (int)(short)(dxy[k] & 0xffff);      // Ix, Iy are 0 for unused slots
+                    const int vy = diff * (dxy[k] >> 16);
                     sx += vx; sy += vy;
                     ax += (unsigned)abs(vx); ay += (unsigned)abs(vy);
                 }
                 // per-chain totals (exact integers) and per-chain sum of |addend|
-                int csx = group_sum(sx, sub, gsize), csy = group_sum(sy, sub, gsize);
-                int cax = group_sum((int)ax, sub, gsize), cay = group_sum((int)ay, sub, gsize);
-                // NOTE |addend| of the SIMD chains is |pair sum| <= |v0|+|v1|, so the bound is conservative
+                const int csx = group_sum(sx, sub, gsize), csy = group_sum(sy, sub, gsize);
+                const int cax = group_sum((int)ax, sub, gsize), cay = group_sum((int)ay, sub, gsize);
+                // |pair sum| <= |v0|+|v1|, so the bound is conservative for the SIMD chains
                 const bool exact = __all_sync(FULL, (sub != 0) || ((unsigned)cax <= (1u << 24) && (unsigned)cay <= (1u << 24)));
-                float fx, fy;      // chain totals as float, valid in lane sub==0 (fast) / sub==gsize-1 (slow)
-                int src_base;
+                float ib1, ib2;
                 if (exact) {
-                    fx = (float)csx; fy = (float)csy; src_base = 0;
+                    // every partial sum of every chain is an exactly representable integer:
+                    // chain totals live in lanes 0, 6, 12, 18 (SIMD) and 24 (tail)
+                    const float fx = (float)csx, fy = (float)csy;
+                    float c0 = __shfl_sync(FULL, fx, 0), c1 = __shfl_sync(FULL, fx, 6), c2 = __shfl_sync(FULL, fx, 12),
+                          c3 = __shfl_sync(FULL, fx, 18), t = __shfl_sync(FULL, fx, 24);
+                    ib1 = __fadd_rn(t, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
+                    c0 = __shfl_sync(FULL, fy, 0); c1 = __shfl_sync(FULL, fy, 6); c2 = __shfl_sync(FULL, fy, 12);
+                    c3 = __shfl_sync(FULL, fy, 18); t = __shfl_sync(FULL, fy, 24);
+                    ib2 = __fadd_rn(t, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
                 } else {
-                    float vx[14], vy[14];
-                    int cnt;
+                    // faithful replay: write the float addends in chain order, runner lanes add them
+                    float* cx = sm.chain + b_slot;
+                    float* cy = sm.chain + CHQ + b_slot;
                     if (!tail) {
 #pragma unroll
                         for (int k = 0; k < 7; k++) {
-                            vx[k] = (float)(pxv[2 * k] + pxv[2 * k + 1]);
-                            vy[k] = (float)(pyv[2 * k] + pyv[2 * k + 1]);
+                            const int d0 = (int)(short)(dpk[k] & 0xffff), d1 = dpk[k] >> 16;
+                            cx[k] = (float)(d0 * (int)(short)(dxy[2 * k] & 0xffff) + d1 * (int)(short)(dxy[2 * k + 1] & 0xffff));
+                            cy[k] = (float)(d0 * (dxy[2 * k] >> 16) + d1 * (dxy[2 * k + 1] >> 16));
                         }
-#pragma unroll
-                        for (int k = 7; k < 14; k++) { vx[k] = 0.f; vy[k] = 0.f; }
-                        cnt = 7;
+                        cx[7] = 0.f; cy[7] = 0.f;
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 14; k++) { vx[k] = (float)pxv[k]; vy[k] = (float)pyv[k]; }
-                        cnt = nel;
+                        for (int k = 0; k < 14; k++) {
+                            const int d = (k & 1) ? (dpk[k >> 1] >> 16) : (int)(short)(dpk[k >> 1] & 0xffff);
+                            cx[k] = (float)(d * (int)(short)(dxy[k] & 0xffff));
+                            cy[k] = (float)(d * (dxy[k] >> 16));
+                        }
                     }
-                    fx = chain_sum(vx, cnt, sub);
-                    fy = chain_sum(vy, cnt, sub);
-                    src_base = -1;   // totals at the last lane of each group
+                    __syncwarp();
+                    const float acc = run_chain(sm.chain, b_base, b_nvec);
+                    ib1 = combine_chains(acc, 0);
+                    ib2 = combine_chains(acc, 1);
+                    __syncwarp();
                 }
-                const int l0 = src_base == 0 ? 0 : 5, l1 = src_base == 0 ? 6 : 11, l2 = src_base == 0 ? 12 : 17,
-                          l3 = src_base == 0 ? 18 : 23, lt = src_base == 0 ? 24 : 31;
-                float q0 = __shfl_sync(FULL, fx, l0), q1 = __shfl_sync(FULL, fx, l1), q2 = __shfl_sync(FULL, fx, l2),
-                      q3 = __shfl_sync(FULL, fx, l3), t = __shfl_sync(FULL, fx, lt);
-                // qb0 = [c0, ., c1, .], qb1 = [c2, ., c3, .]; s = qb0+qb1; ib = tail + ((s0 + 0) + (s2 + 0))
-                float ib1 = __fadd_rn(t, __fadd_rn(__fadd_rn(__fadd_rn(q0, q2), 0.f), __fadd_rn(__fadd_rn(q1, q3), 0.f)));
-                q0 = __shfl_sync(FULL, fy, l0); q1 = __shfl_sync(FULL, fy, l1); q2 = __shfl_sync(FULL, fy, l2);
-                q3 = __shfl_sync(FULL, fy, l3); t = __shfl_sync(FULL, fy, lt);
-                float ib2 = __fadd_rn(t, __fadd_rn(__fadd_rn(__fadd_rn(q0, q2), 0.f), __fadd_rn(__fadd_rn(q1, q3), 0.f)));
-
-                float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
-                float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
-                float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+                const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
+                const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+                const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
                 npx = __fadd_rn(npx, dx); npy = __fadd_rn(npy, dy);
                 nxt.x = __fadd_rn(npx, half); nxt.y = __fadd_rn(npy, half);
                 if ((double)dx * (double)dx + (double)dy * (double)dy <= args.eps2) break;
@@ -427,7 +433,8 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 #pragma unroll
                     for (int k = 0; k < 14; k++) {
                         const uint8_t* s0 = jb + woff[k];
-                        int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv[k];
+                        const int Iv = (k & 1) ? (Ipk[k >> 1] >> 16) : (int)(short)(Ipk[k >> 1] & 0xffff);
+                        const int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
                         if (k < nel) s += abs(diff);
                     }
 #pragma unroll
