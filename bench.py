@@ -190,12 +190,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from visual_odom_b200 import dist as vd
     B = args.units
-    # work-queue scatter: rank 0 owns the unit table (seeds), broadcast over NCCL
-    table = torch.arange(world * B, dtype=torch.int32, device="cuda")
-    if world > 1:
-        dist.broadcast(table, src=0)
-    seeds = table[rank * B:(rank + 1) * B].cpu().tolist()
+    # work-queue scatter: rank 0 owns the unit table (seeds), broadcast over NCCL; unit u -> rank u mod world
+    table = vd.broadcast_unit_table(np.arange(world * B) if rank == 0 else np.zeros(world * B, np.int64), device="cuda")
+    my_units = vd.unit_assignment(world * B, world)[rank]
+    seeds = [int(table[u]) for u in my_units]
     units = [synth.stereo_unit(W_IMG, H_IMG, s) for s in seeds]
 
     # pinned host copies of the images (what a capture / decode thread would hand over)
@@ -257,9 +257,7 @@ def main():
         e2e_ev[s][0].record(stream)
         res_e2e = ctx.frame_batch(arr, pitch)          # H2D + run + D2H, synchronous at return
         if world > 1:                                    # result gather: fixed-size records over NCCL
-            rec = torch.tensor([[r["n_valid"], r["n_inliers"]] for r in res_e2e], dtype=torch.int32, device="cuda")
-            gathered = [torch.empty_like(rec) for _ in range(world)]
-            dist.all_gather(gathered, rec)
+            gathered = vd.gather_records([vd.result_to_record(r) for r in res_e2e], my_units, world * B, device="cuda")
         e2e_ev[s][1].record(stream)
     barrier()
     t_e2e_wall = time.perf_counter() - t_wall0

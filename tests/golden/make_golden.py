@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz from the reference's third-party implementation (cv2 4.13.0)
+driven through the verbatim glue restatement (oracle/ref_path.py, backend="cv2").
+
+Inputs are NOT stored (they are regenerated from the seed by visual_odom_b200.synth); only the
+reference outputs are: selected features, per-call raw LK outputs + status, tracked / valid
+indices, 3-D points, inlier list, rotation, translation -- keyed by config and cv2 version.
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import cv2  # noqa: E402
+from oracle import ref_path  # noqa: E402
+from visual_odom_b200 import synth  # noqa: E402
+
+CONFIGS = {
+    # name: (w, h, seed, scene, n_select, calibration)
+    "kitti_1241x376_n2000_s0": (1241, 376, 0, "v1", 2000, "kitti"),
+    "kitti_1241x376_n500_s7_v0": (1241, 376, 7, "v0", 500, "kitti"),
+    "small_640x240_n300_s11": (640, 240, 11, "v1", 300, "kitti"),
+}
+T_PREV = np.array([0.0, 0.0, -0.8])
+
+
+def reference_outputs(w, h, seed, scene, n_sel, cal):
+    c = synth.KITTI00 if cal == "kitti" else synth.ZED
+    u = synth.stereo_unit(w, h, seed, cal=c, scene=scene)
+    corners = ref_path.fast_cv2(u["l0"])
+    pts = synth.select_features(corners, n_sel)
+    fs = ref_path.FeatureSet(); fs.points = pts.copy(); fs.ages = np.zeros(len(pts), np.int32)
+    cm = ref_path.circular_matching(u["l0"], u["r0"], u["l1"], u["r1"], pts, fs, "cv2")
+    ok = ref_path.check_valid_match(cm["l0"], cm["l0_ret"], 0)
+    pL0, pR0, pL1, pR1 = (ref_path.remove_invalid_points(cm[k], ok) for k in ("l0", "r0", "l1", "r1"))
+    X = ref_path.triangulate(u["P_l"], u["P_r"], pL0, pR0, "cv2")
+    R, t, inl, rvec = ref_path.tracking_frame2frame(u["P_l"], pL0, pL1, X, T_PREV, "cv2")
+    return dict(n_corners=np.int32(len(corners)), corners_head=corners[:64], pts=pts,
+                raw_r0=cm["raw"]["r0"], raw_r1=cm["raw"]["r1"], raw_l1=cm["raw"]["l1"], raw_l0_ret=cm["raw"]["l0_ret"],
+                status=cm["raw"]["status"], kept3=cm["kept_idx"], kept=cm["kept_idx"][ok],
+                l0=pL0, r0=pR0, l1=pL1, r1=pR1, X=X, inliers=inl, R=R, t=t, rvec=rvec,
+                image_crc=np.array([int(np.bitwise_xor.reduce(u[k].astype(np.uint32).ravel() * np.arange(1, w * h + 1, dtype=np.uint32)))
+                                    for k in ("l0", "r0", "l1", "r1")], np.uint32),
+                cv2_version=np.array(cv2.__version__), t_prev=T_PREV)
+
+
+if __name__ == "__main__":
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, cfg in CONFIGS.items():
+        o = reference_outputs(*cfg)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **o)
+        print(name, "corners", int(o["n_corners"]), "tracked", len(o["kept3"]), "valid", len(o["kept"]), "inliers", len(o["inliers"]))

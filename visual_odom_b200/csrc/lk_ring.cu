@@ -81,14 +81,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 #define DW 28                   // row pitch (uint32) of the derivative box
 #define I_ROWS 22
 #define J_ROWS 32
-#define CHQ 448                 // floats per quantity in the chain buffer
+#define CHS 132                 // floats per (quantity, chain) slot: >= 112 and == 4 (mod 32) so that the
+                                // 128-bit loads of the runner lanes fall into distinct bank groups
+#define CHN 15                  // slots: 3 quantities x 5 chains
 struct __align__(128) WarpSmem {
     uint8_t iwin[IW * I_ROWS + 96];     // previous-image window (box 48 x 22)      1056 -> 1152
     uint8_t jtile[IW * J_ROWS];         // next-image tile       (box 48 x 32)      1536
     uint32_t dwin[DW * I_ROWS + 24];    // derivative window     (box 28 x 22 u32)  2464 -> 2560
-    float chain[3 * CHQ];               // chain-ordered float addends (faithful summation)  5376
+    float chain[CHN * CHS];             // chain-ordered float addends (faithful summation)  7920 -> keep 128B multiple below
     uint64_t bar;                       // mbarrier for TMA completion
-    uint64_t pad_[15];
+    uint64_t pad_[1];
 };
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep 128B alignment");
 
@@ -190,11 +192,12 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
         woff[k] = row * IW + col;
     }
     // chain-buffer slots: where this lane writes its addends, and (runner lanes) what it sums
-    const int a_slot = (tail ? 336 : chain * 84) + sub * 14;     // setup: 14 floats per lane and quantity
-    const int b_slot = tail ? 192 + sub * 14 : chain * 48 + sub * 8;   // iteration: 7 pairs (+1 zero) / 14 singles
-    const int rq = lane / 5, rc = lane - rq * 5;                 // runner: quantity, chain
-    const int a_base = rq * CHQ + (rc < 4 ? rc * 84 : 336), a_nvec = lane < 15 ? (rc < 4 ? 21 : 28) : 0;
-    const int b_base = rq * CHQ + (rc < 4 ? rc * 48 : 192), b_nvec = lane < 10 ? (rc < 4 ? 12 : 28) : 0;
+    // slot of (quantity q, chain c) = (5q + c) * CHS
+    const int a_slot = chain * CHS + sub * 14;                   // setup: 14 floats per lane and quantity
+    const int b_slot = chain * CHS + (tail ? sub * 14 : sub * 8);// iteration: 7 pairs (+1 zero) / 14 singles
+    const int rc = lane % 5;                                     // runner lane L sums slot L (quantity L/5, chain L%5)
+    const int a_base = lane * CHS, a_nvec = lane < 15 ? (rc < 4 ? 21 : 28) : 0;
+    const int b_base = lane * CHS, b_nvec = lane < 10 ? (rc < 4 ? 12 : 28) : 0;
 
     if (lane == 0) {
         mbar_init(&sm.bar, 1);
@@ -280,9 +283,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     dxy[k] = (ix & 0xffff) | (iy << 16);
                     const float fx = (float)ix, fy = (float)iy;
                     // chain-ordered addends of A11 / A12 / A22 (zero for the unused tail slots)
-                    sm.chain[0 * CHQ + a_slot + k] = __fmul_rn(fx, fx);
-                    sm.chain[1 * CHQ + a_slot + k] = __fmul_rn(fx, fy);
-                    sm.chain[2 * CHQ + a_slot + k] = __fmul_rn(fy, fy);
+                    sm.chain[0 * 5 * CHS + a_slot + k] = __fmul_rn(fx, fx);
+                    sm.chain[1 * 5 * CHS + a_slot + k] = __fmul_rn(fx, fy);
+                    sm.chain[2 * 5 * CHS + a_slot + k] = __fmul_rn(fy, fy);
                 }
                 __syncwarp();
                 const float acc = run_chain(sm.chain, a_base, a_nvec);
@@ -364,7 +367,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 } else {
                     // faithful replay: write the float addends in chain order, runner lanes add them
                     float* cx = sm.chain + b_slot;
-                    float* cy = sm.chain + CHQ + b_slot;
+                    float* cy = sm.chain + 5 * CHS + b_slot;
                     if (!tail) {
 #pragma unroll
                         for (int k = 0; k < 7; k++) {
