@@ -17,6 +17,8 @@ def built():
     """Native artefacts are built in-tree (nvcc cross-compiles without a GPU)."""
     from visual_odom_b200 import build
     build.build_native()
+    build.build_hostcheck()
+    build.build_facade()
     build.build_oracle()
     return True
 

@@ -70,6 +70,33 @@ def build_native(verbose=False, force=False):
     return LIB
 
 
+FACADE_LIB = os.path.join(ROOT, "libvo_facade.so")
+FACADE_TEST = os.path.join(REPO, "tests", "cpp", "facade_main")
+
+
+def build_facade(force=False):
+    """The reference-signature C++ facade (include/compat/*.h) over libvo_b200.so + its test driver."""
+    src = os.path.join(CSRC, "facade.cpp")
+    inc = os.path.join(REPO, "include", "compat")
+    deps = [src, LIB] + [os.path.join(inc, f) for f in os.listdir(inc)]
+    if force or _newer(deps, FACADE_LIB):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, src, "-o", FACADE_LIB,
+               "-L", ROOT, "-lvo_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("facade build failed")
+    tsrc = os.path.join(REPO, "tests", "cpp", "facade_main.cpp")
+    if force or _newer([tsrc, FACADE_LIB], FACADE_TEST):
+        cmd = ["g++", "-O2", "-std=c++17", "-I", inc, tsrc, "-o", FACADE_TEST, "-L", ROOT, "-lvo_facade", "-lvo_b200",
+               "-Wl,-rpath,$ORIGIN/../../visual_odom_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("facade test driver build failed")
+    return FACADE_LIB
+
+
 def build_hostcheck(force=False):
     """pnp_math.cuh compiled for the host (g++), used by the CPU tests to check the kernels' math."""
     src = os.path.join(CSRC, "host_check.cpp")
@@ -102,4 +129,5 @@ if __name__ == "__main__":
     f = "-f" in sys.argv
     print(build_native(verbose=v, force=f))
     print(build_hostcheck(force=f))
+    print(build_facade(force=f))
     print(build_oracle(force=f))
