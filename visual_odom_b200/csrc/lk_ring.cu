@@ -77,7 +77,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // 16-byte boundary at or below the wanted column and is 16 bytes wider than the data it must hold:
 //   u8 windows  : 48 bytes wide  (<= 15 bytes of lead-in + 22 (I) / 32 (J) bytes of payload)
 //   s16x2 window: 28 elements wide (<= 3 elements of lead-in + 22)
-#define IW 48                   // row pitch of the u8 boxes in shared memory
+#define RAW_W 48                // row pitch of the u8 boxes as TMA writes them (dense)
+#define IW 52                   // row pitch of the u8 windows the kernel reads: 13 words (odd), so the rows a
+                                // warp touches in one LDS fall into different banks (48 = 12 words made rows
+                                // r and r+8 collide: 2.5 wavefronts per byte load, the kernel was LSU bound)
 #define DW 28                   // row pitch (uint32) of the derivative box
 #define I_ROWS 22
 #define J_ROWS 32
@@ -85,17 +88,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                                 // 128-bit loads of the runner lanes fall into distinct bank groups
 #define CHN 15                  // slots: 3 quantities x 5 chains
 struct __align__(128) WarpSmem {
-    uint8_t iwin[IW * I_ROWS + 96];     // previous-image window (box 48 x 22)      1056 -> 1152
-    uint8_t jtile[IW * J_ROWS];         // next-image tile       (box 48 x 32)      1536
     uint32_t dwin[DW * I_ROWS + 24];    // derivative window     (box 28 x 22 u32)  2464 -> 2560
-    float chain[CHN * CHS];             // chain-ordered float addends (faithful summation)  7920 -> keep 128B multiple below
+    uint8_t iwin[IW * I_ROWS + 8];      // previous-image window, pitch 52          1144 -> 1152
+    uint8_t jtile[IW * J_ROWS];         // next-image tile, pitch 52                1664
+    float chain[CHN * CHS];             // chain-ordered float addends (faithful summation); ALSO the landing zone
+                                        // of the dense TMA boxes (I at +0, J at +1152 bytes) before re-pitching
     uint64_t bar;                       // mbarrier for TMA completion
     uint64_t pad_[1];
 };
+#define RAW_I_OFF 0
+#define RAW_J_OFF 1152
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep 128B alignment");
 
-#define I_BYTES (IW * I_ROWS)
-#define J_BYTES (IW * J_ROWS)
+#define I_BYTES (RAW_W * I_ROWS)
+#define J_BYTES (RAW_W * J_ROWS)
 #define D_BYTES (DW * I_ROWS * 4)
 
 // plain-load staging of one box (debug / A-B path): rows x row_bytes from a padded plane
@@ -104,7 +110,17 @@ __device__ __forceinline__ void ldg_box_u8(uint8_t* dst, const uint8_t* plane, i
     const uint8_t* src = plane + (size_t)y * pitch + x;
     for (int r = 0; r < rows; r++) {
         dst[r * IW + lane] = __ldg(src + (size_t)r * pitch + lane);
-        if (lane < IW - 32) dst[r * IW + 32 + lane] = __ldg(src + (size_t)r * pitch + 32 + lane);
+        if (lane < RAW_W - 32) dst[r * IW + 32 + lane] = __ldg(src + (size_t)r * pitch + 32 + lane);
+    }
+}
+// dense TMA box (rows x 48 B) -> window with row pitch IW: each lane moves 16-byte chunks
+__device__ __forceinline__ void repitch(uint8_t* dst, const uint8_t* raw, int rows, int lane)
+{
+    for (int c = lane; c < rows * 3; c += 32) {
+        const int row = c / 3, part = c - row * 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(raw + c * 16);
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + row * IW + part * 16);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
 }
 __device__ __forceinline__ void ldg_box_u32(uint32_t* dst, const uint32_t* plane, int pitch, int x, int y, int lane)
@@ -205,6 +221,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     }
     __syncwarp();
     uint32_t phase = 0;
+    uint8_t* const raw = reinterpret_cast<uint8_t*>(sm.chain);      // landing zone of the dense TMA boxes
 
     const size_t pbase = (size_t)unit * args.cap + f;
     float2 pt = args.pts_in[pbase];
@@ -243,10 +260,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
             if (args.use_tma) {
                 if (lane == 0) {
                     mbar_expect_tx(&sm.bar, I_BYTES + D_BYTES + (j_ok0 ? J_BYTES : 0));
-                    tma_load_3d(sm.iwin, &maps.img_i[level], &sm.bar, ibx, iby, img_prev);
+                    tma_load_3d(raw + RAW_I_OFF, &maps.img_i[level], &sm.bar, ibx, iby, img_prev);
                     tma_load_3d(sm.dwin, &maps.der[level], &sm.bar, dbx, iby, img_prev);
                     if (j_ok0)
-                        tma_load_3d(sm.jtile, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
+                        tma_load_3d(raw + RAW_J_OFF, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
                 }
             } else {
                 ldg_box_u8(sm.iwin, args.img_base[level] + args.plane[level] * img_prev, args.pitch[level], ibx, iby, I_ROWS, lane);
@@ -260,7 +277,12 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
             float a = px - (float)ipx, b = py - (float)ipy;
             int w00, w01, w10, w11;
             bilinear_weights(a, b, w00, w01, w10, w11);
-            if (args.use_tma) { mbar_wait(&sm.bar, phase); phase ^= 1; }
+            if (args.use_tma) {
+                mbar_wait(&sm.bar, phase); phase ^= 1;
+                repitch(sm.iwin, raw + RAW_I_OFF, I_ROWS, lane);
+                if (j_ok0) repitch(sm.jtile, raw + RAW_J_OFF, J_ROWS, lane);
+                __syncwarp();
+            }
 
             // ---- patch extraction: I (x32), Ix, Iy for the 14 owned elements ------------------
             int Ipk[7];           // two int16 patch intensities per register
@@ -315,16 +337,18 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     break;
                 }
                 int rx = inx + VO_PAD - jbx, ry = iny + VO_PAD - jby;   // window origin inside the tile
-                if (!tile_valid || rx < 0 || ry < 0 || rx > IW - 22 || ry > J_ROWS - 22) {
+                if (!tile_valid || rx < 0 || ry < 0 || rx > RAW_W - 22 || ry > J_ROWS - 22) {
                     jbx = (inx - 5 + VO_PAD) & ~15; jby = iny - 5 + VO_PAD;
                     rx = inx + VO_PAD - jbx; ry = 5;
                     __syncwarp();
                     if (args.use_tma) {
                         if (lane == 0) {
                             mbar_expect_tx(&sm.bar, J_BYTES);
-                            tma_load_3d(sm.jtile, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
+                            tma_load_3d(raw + RAW_J_OFF, &maps.img_j[level], &sm.bar, jbx, jby, img_next);
                         }
                         mbar_wait(&sm.bar, phase); phase ^= 1;
+                        repitch(sm.jtile, raw + RAW_J_OFF, J_ROWS, lane);
+                        __syncwarp();
                     } else {
                         ldg_box_u8(sm.jtile, args.img_base[level] + args.plane[level] * img_next, args.pitch[level], jbx, jby, J_ROWS, lane);
                         __syncwarp();
@@ -412,16 +436,18 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     status = 0;
                 } else if (args.err_out) {
                     int rx = inx + VO_PAD - jbx, ry = iny + VO_PAD - jby;
-                    if (!tile_valid || rx < 0 || ry < 0 || rx > IW - 22 || ry > J_ROWS - 22) {
+                    if (!tile_valid || rx < 0 || ry < 0 || rx > RAW_W - 22 || ry > J_ROWS - 22) {
                         jbx = (inx - 5 + VO_PAD) & ~15; jby = iny - 5 + VO_PAD;
                         rx = inx + VO_PAD - jbx; ry = 5;
                         __syncwarp();
                         if (args.use_tma) {
                             if (lane == 0) {
                                 mbar_expect_tx(&sm.bar, J_BYTES);
-                                tma_load_3d(sm.jtile, &maps.img_j[0], &sm.bar, jbx, jby, img_next);
+                                tma_load_3d(raw + RAW_J_OFF, &maps.img_j[0], &sm.bar, jbx, jby, img_next);
                             }
                             mbar_wait(&sm.bar, phase); phase ^= 1;
+                            repitch(sm.jtile, raw + RAW_J_OFF, J_ROWS, lane);
+                            __syncwarp();
                         } else {
                             ldg_box_u8(sm.jtile, args.img_base[0] + args.plane[0] * img_next, args.pitch[0], jbx, jby, J_ROWS, lane);
                             __syncwarp();
