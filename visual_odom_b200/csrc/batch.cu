@@ -34,45 +34,106 @@ extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const 
     return VO_OK;
 }
 
-extern "C" int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch)
+// H2D of units [u0, u0+n) on stream `st`; scalars go through the pinned staging block (disjoint per unit)
+static int upload_range(vo_ctx* ctx, const vo_unit* units, int u0, int n, size_t pitch, cudaStream_t st, bool detect)
+{
+    const int w = ctx->w, h = ctx->h, cap = ctx->cap;
+    const int total = ctx->batch_units;
+    double* h_tprev = (double*)ctx->h_pinned;
+    int* h_cnt = (int*)(h_tprev + 3 * (size_t)total);
+    for (int u = u0; u < u0 + n; u++) {
+        const vo_unit& U = units[u];
+        const uint8_t* imgs[4] = {U.l0, U.r0, U.l1, U.r1};
+        for (int k = 0; k < 4; k++) {
+            uint8_t* dst = ctx->d_raw + ((size_t)u * 4 + k) * w * h;
+            if (pitch == (size_t)w) VO_CUDA_CHECK(cudaMemcpyAsync(dst, imgs[k], (size_t)w * h, cudaMemcpyHostToDevice, st));
+            else VO_CUDA_CHECK(cudaMemcpy2DAsync(dst, w, imgs[k], pitch, w, h, cudaMemcpyHostToDevice, st));
+        }
+        if (!detect && U.n_pts > 0)
+            VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in + (size_t)u * cap, U.pts, (size_t)U.n_pts * sizeof(float2),
+                                          cudaMemcpyHostToDevice, st));
+        h_cnt[u] = U.n_pts;
+        for (int k = 0; k < 3; k++) h_tprev[3 * u + k] = U.t_prev[k];
+    }
+    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tprev + 3 * (size_t)u0, h_tprev + 3 * (size_t)u0, (size_t)n * 3 * sizeof(double),
+                                  cudaMemcpyHostToDevice, st));
+    VO_CUDA_CHECK(cudaMemcpyAsync((detect ? ctx->d_want : ctx->d_npts) + u0, h_cnt + u0, (size_t)n * sizeof(int),
+                                  cudaMemcpyHostToDevice, st));
+    return VO_OK;
+}
+
+static int validate_units(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch, bool* detect_out, int* max_pts_out)
 {
     if (!ctx || !units) return VO_E_INVALID;
     if (n_units <= 0 || n_units > ctx->batch_units) { vo_set_error(ctx, "n_units=%d outside the configured batch (%d)", n_units, ctx->batch_units); return VO_E_INVALID; }
     if (pitch < (size_t)ctx->w) { vo_set_error(ctx, "pitch %zu < width %d", pitch, ctx->w); return VO_E_INVALID; }
-    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    const int w = ctx->w, h = ctx->h, cap = ctx->cap;
-    // small per-unit scalars go through one pinned staging block
-    const size_t stage_bytes = (size_t)n_units * (2 * sizeof(int) + 3 * sizeof(double));
-    int rc = vo_ensure_pinned(ctx, stage_bytes + 64);
-    if (rc) return rc;
-    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // staging block may still be in flight
-    double* h_tprev = (double*)ctx->h_pinned;
-    int* h_npts = (int*)(h_tprev + 3 * (size_t)n_units);
-    int* h_want = h_npts + n_units;
-    bool detect = (units[0].pts == nullptr);
+    const bool detect = (units[0].pts == nullptr);
     int max_pts = 0;
     for (int u = 0; u < n_units; u++) {
         const vo_unit& U = units[u];
         if (!U.l0 || !U.r0 || !U.l1 || !U.r1) { vo_set_error(ctx, "unit %d: null image", u); return VO_E_INVALID; }
         if ((U.pts == nullptr) != detect) { vo_set_error(ctx, "units must all carry features or all request detection"); return VO_E_INVALID; }
-        if (U.n_pts < 0 || U.n_pts > cap) { vo_set_error(ctx, "unit %d: n_pts=%d outside [0,%d]", u, U.n_pts, cap); return VO_E_CAPACITY; }
-        const uint8_t* imgs[4] = {U.l0, U.r0, U.l1, U.r1};
-        for (int k = 0; k < 4; k++)
-            VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_raw + ((size_t)u * 4 + k) * w * h, w, imgs[k], pitch, w, h,
-                                            cudaMemcpyHostToDevice, ctx->stream));
-        if (!detect && U.n_pts > 0)
-            VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in + (size_t)u * cap, U.pts, (size_t)U.n_pts * sizeof(float2),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-        h_npts[u] = U.n_pts; h_want[u] = U.n_pts;
-        for (int k = 0; k < 3; k++) h_tprev[3 * u + k] = U.t_prev[k];
+        if (U.n_pts < 0 || U.n_pts > ctx->cap) { vo_set_error(ctx, "unit %d: n_pts=%d outside [0,%d]", u, U.n_pts, ctx->cap); return VO_E_CAPACITY; }
         if (U.n_pts > max_pts) max_pts = U.n_pts;
     }
-    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tprev, h_tprev, (size_t)n_units * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(detect ? ctx->d_want : ctx->d_npts, detect ? h_want : h_npts, (size_t)n_units * sizeof(int),
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    *detect_out = detect; *max_pts_out = max_pts;
+    // pinned staging: t_prev, counts, result records
+    const size_t bytes = (size_t)ctx->batch_units * (3 * sizeof(double) + sizeof(int) + sizeof(vo_unit_result_dev)) + 256;
+    return vo_ensure_pinned(ctx, bytes);
+}
+
+static vo_unit_result_dev* pinned_results(vo_ctx* ctx)
+{
+    char* p = (char*)ctx->h_pinned + (size_t)ctx->batch_units * (3 * sizeof(double) + sizeof(int));
+    p = (char*)(((uintptr_t)p + 63) & ~(uintptr_t)63);
+    return (vo_unit_result_dev*)p;
+}
+
+extern "C" int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch)
+{
+    bool detect; int max_pts;
+    int rc = validate_units(ctx, units, n_units, pitch, &detect, &max_pts);
+    if (rc) return rc;
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // staging block may still be in flight
+    if ((rc = upload_range(ctx, units, 0, n_units, pitch, ctx->stream, detect))) return rc;
     ctx->batch_uploaded = n_units;
     ctx->batch_detect = detect;
     ctx->batch_max_pts = max_pts;
+    return VO_OK;
+}
+
+static int ensure_side_streams(vo_ctx* ctx)
+{
+    if (ctx->fork_ev) return VO_OK;
+    VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    for (int c = 0; c < 2; c++) {
+        VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side_stream[c], cudaStreamNonBlocking));
+        VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->join_ev[c], cudaEventDisableTiming));
+    }
+    return VO_OK;
+}
+
+// the whole path for the resident units of `v`, asynchronous on v.s
+static int run_range(vo_ctx* ctx, const View& v)
+{
+    ctx->imgs_per_unit = 4;
+    int rc;
+    if (ctx->batch_detect) {
+        if ((rc = vo_run_fast(ctx, v, 0, false))) return rc;
+        if ((rc = vo_run_select(ctx, v))) return rc;
+    }
+    const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};      // ring L0->R0->R1->L1->L0 (planes L0,R0,L1,R1)
+    if ((rc = vo_run_lk(ctx, v, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, v, false))) return rc;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    if ((rc = vo_run_triangulate(ctx, v, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
+    if ((rc = vo_run_pnp(ctx, v, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
+    k_pack_counts<<<(v.n + 63) / 64, 64, 0, v.s>>>(ctx->d_results + v.u0, ctx->d_npts + v.u0, ctx->d_ndet + v.u0, ctx->d_n3 + v.u0,
+                                                  ctx->d_n5 + v.u0, v.n, ctx->batch_detect ? 1 : 0);
+    ctx->launches += 1;
+    VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }
 
@@ -83,24 +144,21 @@ extern "C" int vo_batch_run(vo_ctx* ctx)
     if (units <= 0) { vo_set_error(ctx, "vo_batch_run: nothing uploaded"); return VO_E_INVALID; }
     if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_run: projection matrices not set"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    ctx->imgs_per_unit = 4;
-    int rc;
-    if (ctx->batch_detect) {
-        if ((rc = vo_run_fast(ctx, units, 0, false))) return rc;
-        ctx->launches += vo_launch_select(ctx->d_corners, ctx->corner_cap, ctx->d_ndet, ctx->d_want, ctx->d_pts_in, ctx->cap,
-                                          ctx->d_npts, units, ctx->stream);
+    if (units < 2) return run_range(ctx, View{0, units, ctx->stream});
+    // two unit ranges on two side streams: the latency-bound PnP kernels of one range run under the
+    // LK ring of the other (fork from / join into the context's stream, so callers see one stream)
+    int rc = ensure_side_streams(ctx);
+    if (rc) return rc;
+    VO_CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    const int half = (units + 1) / 2;
+    for (int c = 0; c < 2; c++) {
+        const int u0 = c ? half : 0, n = c ? units - half : half;
+        cudaStream_t st = ctx->side_stream[c];
+        VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+        if ((rc = run_range(ctx, View{u0, n, st}))) return rc;
+        VO_CUDA_CHECK(cudaEventRecord(ctx->join_ev[c], st));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c], 0));
     }
-    const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};
-    if ((rc = vo_run_lk(ctx, units, 4, ip, in, false))) return rc;
-    if ((rc = vo_run_filter(ctx, units, false))) return rc;
-    const size_t cs = (size_t)ctx->units * ctx->cap;
-    if ((rc = vo_run_triangulate(ctx, units, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
-    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
-    if ((rc = vo_run_pnp(ctx, units, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
-    k_pack_counts<<<(units + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_results, ctx->d_npts, ctx->d_ndet, ctx->d_n3, ctx->d_n5, units,
-                                                             ctx->batch_detect ? 1 : 0);
-    ctx->launches += 1;
-    VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }
 
@@ -115,12 +173,43 @@ extern "C" int vo_batch_download(vo_ctx* ctx, vo_unit_result* results, int n_uni
     return VO_OK;
 }
 
+// End-to-end entry point: H2D + whole path + D2H.  The batch is split into two unit ranges on two
+// side streams forked from / joined into the context's stream, so the H2D of the second range runs
+// under the kernels of the first (the images arrive over PCIe; compute is ~6x longer than the copy).
 extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch, vo_unit_result* results)
 {
-    int rc = vo_batch_upload(ctx, units, n_units, pitch);
+    bool detect; int max_pts;
+    int rc = validate_units(ctx, units, n_units, pitch, &detect, &max_pts);
     if (rc) return rc;
-    if ((rc = vo_batch_run(ctx))) return rc;
-    return vo_batch_download(ctx, results, n_units);
+    if (!results) return VO_E_INVALID;
+    if (!ctx->have_P) { vo_set_error(ctx, "vo_frame_batch: projection matrices not set"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->batch_uploaded = n_units; ctx->batch_detect = detect; ctx->batch_max_pts = max_pts;
+    vo_unit_result_dev* h_res = pinned_results(ctx);
+    const int nchunks = n_units >= 2 ? 2 : 1;
+    if (nchunks == 1) {
+        if ((rc = upload_range(ctx, units, 0, n_units, pitch, ctx->stream, detect))) return rc;
+        if ((rc = run_range(ctx, View{0, n_units, ctx->stream}))) return rc;
+        VO_CUDA_CHECK(cudaMemcpyAsync(h_res, ctx->d_results, (size_t)n_units * sizeof(vo_unit_result_dev), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        if ((rc = ensure_side_streams(ctx))) return rc;
+        VO_CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+        const int half = (n_units + 1) / 2;
+        for (int c = 0; c < 2; c++) {
+            const int u0 = c ? half : 0, n = c ? n_units - half : half;
+            cudaStream_t st = ctx->side_stream[c];
+            VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+            if ((rc = upload_range(ctx, units, u0, n, pitch, st, detect))) return rc;
+            if ((rc = run_range(ctx, View{u0, n, st}))) return rc;
+            VO_CUDA_CHECK(cudaMemcpyAsync(h_res + u0, ctx->d_results + u0, (size_t)n * sizeof(vo_unit_result_dev), cudaMemcpyDeviceToHost, st));
+            VO_CUDA_CHECK(cudaEventRecord(ctx->join_ev[c], st));
+            VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c], 0));
+        }
+    }
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(results, h_res, (size_t)n_units * sizeof(vo_unit_result));
+    return VO_OK;
 }
 
 extern "C" int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,

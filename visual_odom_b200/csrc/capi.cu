@@ -34,7 +34,7 @@ extern "C" int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in, prev_pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_npts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     const int ip[1] = {0}, in[1] = {1};
-    rc = vo_run_lk(ctx, 1, 1, ip, in, err != nullptr);
+    rc = vo_run_lk(ctx, View{0, 1, ctx->stream}, 1, ip, in, err != nullptr);
     ctx->imgs_per_unit = 4;
     if (rc) return rc;
     VO_CUDA_CHECK(cudaMemcpyAsync(next_pts, ctx->d_pts_out, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -68,8 +68,8 @@ extern "C" int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* 
         VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_ages_in, ages_io, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     // ring order: L0->R0, R0->R1, R1->L1, L1->L0   (planes: L0=0, R0=1, L1=2, R1=3)
     const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};
-    if ((rc = vo_run_lk(ctx, 1, 4, ip, in, false))) return rc;
-    if ((rc = vo_run_filter(ctx, 1, ages_io != nullptr))) return rc;
+    if ((rc = vo_run_lk(ctx, View{0, 1, ctx->stream}, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, View{0, 1, ctx->stream}, ages_io != nullptr))) return rc;
     int n3 = 0;
     VO_CUDA_CHECK(cudaMemcpyAsync(&n3, ctx->d_n3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     const size_t cs = (size_t)ctx->units * ctx->cap;
@@ -110,7 +110,7 @@ extern "C" int vo_fast_detect(vo_ctx* ctx, const uint8_t* img, int w, int h, siz
     if ((rc = vo_ensure_state(ctx, w, h, 1, 4))) return rc;
     ctx->imgs_per_unit = 4;
     if ((rc = upload_image(ctx, 0, img, w, h, pitch))) return rc;
-    if ((rc = vo_run_fast(ctx, 1, 0, response != nullptr))) return rc;
+    if ((rc = vo_run_fast(ctx, View{0, 1, ctx->stream}, 0, response != nullptr))) return rc;
     int n = 0;
     VO_CUDA_CHECK(cudaMemcpyAsync(&n, ctx->d_ndet, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -142,7 +142,7 @@ extern "C" int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4, pts_l, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4 + cs, pts_r, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n5, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = vo_run_triangulate(ctx, 1, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    if ((rc = vo_run_triangulate(ctx, View{0, 1, ctx->stream}, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
     VO_CUDA_CHECK(cudaMemcpyAsync(X, ctx->d_X, (size_t)n * sizeof(float3), cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return VO_OK;
@@ -171,7 +171,7 @@ extern "C" int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f*
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4 + 2 * cs, x, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_n5, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tprev, tvec_io, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = vo_run_pnp(ctx, 1, ctx->d_valid4 + 2 * cs, ctx->d_n5, K))) return rc;
+    if ((rc = vo_run_pnp(ctx, View{0, 1, ctx->stream}, ctx->d_valid4 + 2 * cs, ctx->d_n5, K))) return rc;
     vo_unit_result_dev r;
     VO_CUDA_CHECK(cudaMemcpyAsync(&r, ctx->d_results, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -77,6 +77,11 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     vo_free_state(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int c = 0; c < 2; c++) {
+        if (ctx->join_ev[c]) cudaEventDestroy(ctx->join_ev[c]);
+        if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
+    }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -273,19 +278,26 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
 }
 
 // ---------------------------------------------------------------------------------------------
-int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int* img_next, bool want_err)
+int vo_run_lk(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err)
 {
+    const int ipu = ctx->imgs_per_unit;
+    const size_t uo = (size_t)v.u0 * ctx->cap;
     PyrGeom pg = ctx->pg;
-    pg.n_img = units * ctx->imgs_per_unit;
-    ctx->launches += vo_launch_pyramid(pg, ctx->d_raw_tab, ctx->w, ctx->stream);
+    pg.n_img = v.n * ipu;
+    for (int l = 0; l < pg.nlevels; l++) {
+        pg.lv[l].img += (size_t)v.u0 * ipu * pg.lv[l].plane;
+        pg.lv[l].der += (size_t)v.u0 * ipu * pg.lv[l].plane;
+    }
+    ctx->launches += vo_launch_pyramid(pg, ctx->d_raw_tab + (size_t)v.u0 * ipu, ctx->w, v.s);
     VO_CUDA_CHECK(cudaGetLastError());
 
     LkArgs a;
     memset(&a, 0, sizeof(a));
-    a.n_units = units;
+    a.n_units = v.n;
     a.cap = ctx->cap;
-    a.n_pts = ctx->d_npts;
-    a.imgs_per_unit = ctx->imgs_per_unit;
+    a.n_pts = ctx->d_npts + v.u0;
+    a.imgs_per_unit = ipu;
+    a.img_plane0 = v.u0 * ipu;
     a.ncalls = ncalls;
     for (int c = 0; c < ncalls; c++) { a.img_prev[c] = img_prev[c]; a.img_next[c] = img_next[c]; }
     a.nlevels = pg.nlevels;
@@ -295,14 +307,14 @@ int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int
     if (eps < 0.) eps = 0.; if (eps > 10.) eps = 10.;
     a.eps2 = eps * eps;
     a.min_eig = ctx->p.lk_min_eig;
-    a.pts_in = ctx->d_pts_in;
-    a.pts_out = ctx->d_pts_out;
-    a.status_out = ctx->d_status;
-    a.err_out = want_err ? ctx->d_err : nullptr;
+    a.pts_in = ctx->d_pts_in + uo;
+    a.pts_out = ctx->d_pts_out + uo;
+    a.status_out = ctx->d_status + uo;
+    a.err_out = want_err ? ctx->d_err + uo : nullptr;
     a.call_stride = (size_t)ctx->units * ctx->cap;
     a.use_tma = ctx->lk_use_tma ? 1 : 0;
-    for (int l = 0; l < pg.nlevels; l++) {
-        a.img_base[l] = pg.lv[l].img; a.der_base[l] = pg.lv[l].der;
+    for (int l = 0; l < pg.nlevels; l++) {      // absolute plane bases (indexed with the absolute plane number)
+        a.img_base[l] = ctx->pg.lv[l].img; a.der_base[l] = ctx->pg.lv[l].der;
         a.pitch[l] = pg.lv[l].pitch; a.plane[l] = pg.lv[l].plane;
     }
 
@@ -316,82 +328,98 @@ int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int
         }
         e0 = ctx->ev_pool[ctx->ev_used]; e1 = ctx->ev_pool[ctx->ev_used + 1];
         ctx->ev_used += 2;
-        VO_CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+        VO_CUDA_CHECK(cudaEventRecord(e0, v.s));
     }
-    VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->stream));
+    VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, v.s));
     ctx->launches += 1;
-    if (e1) VO_CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+    if (e1) VO_CUDA_CHECK(cudaEventRecord(e1, v.s));
     return VO_OK;
 }
 
-int vo_run_filter(vo_ctx* ctx, int units, bool with_ages)
+int vo_run_filter(vo_ctx* ctx, const View& v, bool with_ages)
 {
+    const size_t uo = (size_t)v.u0 * ctx->cap;
     FilterArgs f;
     memset(&f, 0, sizeof(f));
     f.cap = ctx->cap;
     f.call_stride = (size_t)ctx->units * ctx->cap;
     f.circ_threshold = ctx->p.circ_threshold;
-    f.n_pts = ctx->d_npts;
-    f.pts_in = ctx->d_pts_in;
-    f.pts_out = ctx->d_pts_out;
-    f.status = ctx->d_status;
-    f.ages_in = with_ages ? ctx->d_ages_in : nullptr;
-    f.ages_out = ctx->d_ages_out;
-    f.kept5 = ctx->d_kept5;
-    f.idx3 = ctx->d_idx3;
-    f.n3 = ctx->d_n3;
-    f.valid4 = ctx->d_valid4;
-    f.idx5 = ctx->d_idx5;
-    f.n5 = ctx->d_n5;
-    VO_CUDA_CHECK(vo_launch_ring_filter(f, units, ctx->stream));
+    f.n_pts = ctx->d_npts + v.u0;
+    f.pts_in = ctx->d_pts_in + uo;
+    f.pts_out = ctx->d_pts_out + uo;
+    f.status = ctx->d_status + uo;
+    f.ages_in = with_ages ? ctx->d_ages_in + uo : nullptr;
+    f.ages_out = ctx->d_ages_out + uo;
+    f.kept5 = ctx->d_kept5 + uo;
+    f.idx3 = ctx->d_idx3 + uo;
+    f.n3 = ctx->d_n3 + v.u0;
+    f.valid4 = ctx->d_valid4 + uo;
+    f.idx5 = ctx->d_idx5 + uo;
+    f.n5 = ctx->d_n5 + v.u0;
+    VO_CUDA_CHECK(vo_launch_ring_filter(f, v.n, v.s));
     ctx->launches += 1;
     return VO_OK;
 }
 
-
-int vo_run_fast(vo_ctx* ctx, int units, int plane_in_unit, bool want_resp)
+int vo_run_fast(vo_ctx* ctx, const View& v, int plane_in_unit, bool want_resp)
 {
     FastArgs a;
     memset(&a, 0, sizeof(a));
-    a.n_units = units;
-    a.img_tab = ctx->d_raw_tab + plane_in_unit;
+    const size_t plane = (size_t)ctx->w * ctx->h;
+    a.n_units = v.n;
+    a.img_tab = ctx->d_raw_tab + (size_t)v.u0 * ctx->imgs_per_unit + plane_in_unit;
     a.img_stride_idx = ctx->imgs_per_unit;
     a.w = ctx->w; a.h = ctx->h; a.pitch = ctx->w;
     a.threshold = ctx->p.fast_threshold; a.nonmax = ctx->p.fast_nonmax;
-    a.score = ctx->d_score; a.score_plane = (size_t)ctx->w * ctx->h;
-    a.rowbuf = ctx->d_rowbuf; a.rowcap = ctx->w;
-    a.rowcount = ctx->d_rowcount; a.rowoff = ctx->d_rowoff; a.n_det = ctx->d_ndet;
-    a.corners = ctx->d_corners; a.resp = want_resp ? ctx->d_resp : nullptr; a.corner_cap = ctx->corner_cap;
-    ctx->launches += vo_launch_fast(a, ctx->stream);
+    a.score = ctx->d_score + v.u0 * plane; a.score_plane = plane;
+    a.rowbuf = ctx->d_rowbuf + v.u0 * plane; a.rowcap = ctx->w;
+    a.rowcount = ctx->d_rowcount + (size_t)v.u0 * ctx->h; a.rowoff = ctx->d_rowoff + (size_t)v.u0 * ctx->h;
+    a.n_det = ctx->d_ndet + v.u0;
+    a.corners = ctx->d_corners + (size_t)v.u0 * ctx->corner_cap;
+    a.resp = want_resp ? ctx->d_resp + (size_t)v.u0 * ctx->corner_cap : nullptr;
+    a.corner_cap = ctx->corner_cap;
+    ctx->launches += vo_launch_fast(a, v.s);
     VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }
 
-int vo_run_triangulate(vo_ctx* ctx, int units, const float2* pts_l, const float2* pts_r, const int* n)
+int vo_run_select(vo_ctx* ctx, const View& v)
 {
+    ctx->launches += vo_launch_select(ctx->d_corners + (size_t)v.u0 * ctx->corner_cap, ctx->corner_cap, ctx->d_ndet + v.u0,
+                                      ctx->d_want + v.u0, ctx->d_pts_in + (size_t)v.u0 * ctx->cap, ctx->cap, ctx->d_npts + v.u0,
+                                      v.n, v.s);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n)
+{
+    const size_t uo = (size_t)v.u0 * ctx->cap;
     TriArgs t;
     memset(&t, 0, sizeof(t));
-    t.cap = ctx->cap; t.n_pts = n; t.pts_l = pts_l; t.pts_r = pts_r; t.X = ctx->d_X;
+    t.cap = ctx->cap; t.n_pts = n + v.u0; t.pts_l = pts_l + uo; t.pts_r = pts_r + uo; t.X = ctx->d_X + uo;
     for (int k = 0; k < 12; k++) { t.Pl[k] = (double)ctx->P_l[k]; t.Pr[k] = (double)ctx->P_r[k]; }
-    ctx->launches += vo_launch_triangulate(t, units, ctx->stream);
+    ctx->launches += vo_launch_triangulate(t, v.n, v.s);
     VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }
 
-int vo_run_pnp(vo_ctx* ctx, int units, const float2* pts2d, const int* n, const float* K9)
+int vo_run_pnp(vo_ctx* ctx, const View& v, const float2* pts2d, const int* n, const float* K9)
 {
+    const size_t uo = (size_t)v.u0 * ctx->cap, its = (size_t)ctx->p.pnp_iterations;
     PnpArgs a;
     memset(&a, 0, sizeof(a));
-    a.n_units = units; a.cap = ctx->cap; a.iterations = ctx->p.pnp_iterations;
-    a.n_pts = n; a.X = ctx->d_X; a.x = pts2d;
+    a.n_units = v.n; a.cap = ctx->cap; a.iterations = ctx->p.pnp_iterations;
+    a.n_pts = n + v.u0; a.X = ctx->d_X + uo; a.x = pts2d + uo;
     a.fu = (double)K9[0]; a.fv = (double)K9[4]; a.uc = (double)K9[2]; a.vc = (double)K9[5];
     const double thr = (double)ctx->p.pnp_reproj_error;      // float -> double, squared in double, stored float
     a.thr2 = (float)(thr * thr);
     a.confidence = ctx->p.pnp_confidence;
-    a.t_prev = ctx->d_tprev;
-    a.state = ctx->d_pnp_state; a.subsets = ctx->d_subsets; a.models = ctx->d_models; a.counts = ctx->d_counts;
-    a.inliers = ctx->d_inliers; a.results = ctx->d_results;
-    ctx->launches += vo_launch_pnp(a, ctx->stream);
+    a.t_prev = ctx->d_tprev + (size_t)v.u0 * 3;
+    a.state = ctx->d_pnp_state + v.u0; a.subsets = ctx->d_subsets + v.u0 * its * 5; a.models = ctx->d_models + v.u0 * its * 12;
+    a.counts = ctx->d_counts + v.u0 * its;
+    a.inliers = ctx->d_inliers + uo; a.results = ctx->d_results + v.u0;
+    ctx->launches += vo_launch_pnp(a, v.s);
     VO_CUDA_CHECK(cudaGetLastError());
     return VO_OK;
 }

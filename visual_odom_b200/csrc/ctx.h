@@ -81,17 +81,22 @@ struct vo_ctx {
     int batch_uploaded = 0;         // units currently resident
     bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
+    cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
 };
 
 void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
 int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
 void vo_free_state(vo_ctx* ctx);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
-// run pyramids + LK (ncalls chained) for `units` units; images must already be in d_raw/d_raw_tab
-int vo_run_lk(vo_ctx* ctx, int units, int ncalls, const int* img_prev, const int* img_next, bool want_err);
-int vo_run_filter(vo_ctx* ctx, int units, bool with_ages);
-// FAST on raw plane `plane_in_unit` of each unit -> d_corners / d_ndet
-int vo_run_fast(vo_ctx* ctx, int units, int plane_in_unit, bool want_resp);
+// a contiguous range of resident work units processed on one stream
+struct View { int u0, n; cudaStream_t s; };
+// run pyramids + LK (ncalls chained) for the units of `v`; images must already be in d_raw/d_raw_tab
+int vo_run_lk(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err);
+int vo_run_filter(vo_ctx* ctx, const View& v, bool with_ages);
+// FAST on raw plane `plane_in_unit` of each unit -> d_corners / d_ndet ; stride selection -> d_pts_in / d_npts
+int vo_run_fast(vo_ctx* ctx, const View& v, int plane_in_unit, bool want_resp);
+int vo_run_select(vo_ctx* ctx, const View& v);
 // triangulate pts_l/pts_r ([units][cap], counts n) -> d_X ; PnP on (d_X, pts2d) -> d_results / d_inliers
-int vo_run_triangulate(vo_ctx* ctx, int units, const float2* pts_l, const float2* pts_r, const int* n);
-int vo_run_pnp(vo_ctx* ctx, int units, const float2* pts2d, const int* n, const float* K9);
+int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n);
+int vo_run_pnp(vo_ctx* ctx, const View& v, const float2* pts2d, const int* n, const float* K9);

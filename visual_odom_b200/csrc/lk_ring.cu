@@ -230,8 +230,8 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     const int max_level = args.nlevels - 1;
 
     for (int call = 0; call < args.ncalls; call++) {
-        const int img_prev = unit * args.imgs_per_unit + args.img_prev[call];
-        const int img_next = unit * args.imgs_per_unit + args.img_next[call];
+        const int img_prev = args.img_plane0 + unit * args.imgs_per_unit + args.img_prev[call];
+        const int img_next = args.img_plane0 + unit * args.imgs_per_unit + args.img_next[call];
         float2 nxt = make_float2(0.f, 0.f);
         int status = 1;
         float errv = 0.f;

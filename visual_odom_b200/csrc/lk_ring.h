@@ -16,6 +16,7 @@ struct LkArgs {
     int cap;                // feature capacity per unit (stride of the point arrays)
     const int* n_pts;       // [n_units] live feature count per unit (device) or nullptr = cap
     int imgs_per_unit;      // planes per unit in the pyramid (4 for the ring, 2 for a single call)
+    int img_plane0;         // absolute plane index of this launch's first unit (unit-range launches)
     int ncalls;             // chained calcOpticalFlowPyrLK calls (4 for the ring)
     int img_prev[4];        // plane index (within the unit) of prev image per call
     int img_next[4];        // plane index of next image per call
