@@ -242,9 +242,25 @@ def main():
     barrier()
     t_dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = ctx.kernel_launches() - launches0
-    lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
     res = ctx.batch_download(B)
     feats_per_launch = sum(r["n_features"] for r in res)
+
+    # ---------------- LK kernel alone (roofline): one stream, so its CUDA-event time is not shared ----------------
+    ctx.set_option("batch_streams", 1)
+    for _ in range(args.warmup):
+        ctx.batch_run()
+    torch.cuda.synchronize()
+    ctx.lk_kernel_time(reset=True)
+    ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev1[s][0].record(stream)
+        ctx.batch_run()
+        ev1[s][1].record(stream)
+    torch.cuda.synchronize()
+    t_single_ms = sum(a.elapsed_time(b) for a, b in ev1)
+    lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
+    ctx.set_option("batch_streams", 2)
 
     # ---------------- end-to-end through the C-ABI with host buffers (`e2e`) ----------------
     for _ in range(max(1, args.warmup)):
@@ -301,7 +317,8 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_lk_ring", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "features_per_launch": feats_per_launch,
-                         "avg_launch_ms": lk_avg_ms, "lk_share_of_step": lk_ms / t_dev_ms if t_dev_ms else None,
+                         "avg_launch_ms": lk_avg_ms, "lk_share_of_step": lk_ms / t_single_ms if t_single_ms else None,
+                         "single_stream_ms_per_step": t_single_ms / args.steps,
                          "note": "algorithmic bytes per SURVEY.md 8(d); the kernel is ALU/latency bound, see DESIGN.md"},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{args.cpu_sample} frames of the same workload in {cpu_dt:.1f} s; cv2 (the OpenCV the "

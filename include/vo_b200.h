@@ -76,6 +76,9 @@ VO_API long long vo_kernel_launches(const vo_ctx* ctx);
 /* Accumulated device time (ms) of the LK ring kernel launches since the last reset,
  * measured with CUDA events on the launching stream; n = launches counted. */
 VO_API int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset);
+/* Run-time knobs (measurement / debugging): "batch_streams" = 1|2 (unit ranges the batched path runs
+ * concurrently, default 2), "lk_staging" = 0 (TMA, default) | 1 (plain loads). */
+VO_API int vo_set_option(vo_ctx* ctx, const char* key, double value);
 
 /* ---- A1: cv::FAST(image, kps, threshold, nonmax) + KeyPoint::convert ------------------------
  * replaces featureDetectionFast(), reference src/feature.cpp:39-47 (decl feature.h:48).

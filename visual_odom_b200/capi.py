@@ -55,6 +55,7 @@ SIGNATURES = {
     "vo_sync": (C.c_int, [C.c_void_p]),
     "vo_kernel_launches": (C.c_longlong, [C.c_void_p]),
     "vo_lk_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
+    "vo_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "vo_fast_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
                                  C.c_int, C.POINTER(C.c_int)]),
     "vo_lk_track": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
@@ -149,6 +150,9 @@ class Context:
 
     def sync(self):
         self._check(self.lib.vo_sync(self.h))
+
+    def set_option(self, key, value):
+        self._check(self.lib.vo_set_option(self.h, key.encode(), float(value)))
 
     def kernel_launches(self):
         return int(self.lib.vo_kernel_launches(self.h))

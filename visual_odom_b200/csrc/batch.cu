@@ -144,7 +144,7 @@ extern "C" int vo_batch_run(vo_ctx* ctx)
     if (units <= 0) { vo_set_error(ctx, "vo_batch_run: nothing uploaded"); return VO_E_INVALID; }
     if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_run: projection matrices not set"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    if (units < 2) return run_range(ctx, View{0, units, ctx->stream});
+    if (units < 2 || ctx->batch_streams < 2) return run_range(ctx, View{0, units, ctx->stream});
     // two unit ranges on two side streams: the latency-bound PnP kernels of one range run under the
     // LK ring of the other (fork from / join into the context's stream, so callers see one stream)
     int rc = ensure_side_streams(ctx);
@@ -187,7 +187,7 @@ extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, si
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->batch_uploaded = n_units; ctx->batch_detect = detect; ctx->batch_max_pts = max_pts;
     vo_unit_result_dev* h_res = pinned_results(ctx);
-    const int nchunks = n_units >= 2 ? 2 : 1;
+    const int nchunks = (n_units >= 2 && ctx->batch_streams >= 2) ? 2 : 1;
     if (nchunks == 1) {
         if ((rc = upload_range(ctx, units, 0, n_units, pitch, ctx->stream, detect))) return rc;
         if ((rc = run_range(ctx, View{0, n_units, ctx->stream}))) return rc;

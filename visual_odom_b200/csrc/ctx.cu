@@ -104,6 +104,15 @@ extern "C" int vo_sync(vo_ctx* ctx)
     return VO_OK;
 }
 
+extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
+{
+    if (!ctx || !key) return VO_E_INVALID;
+    if (strcmp(key, "batch_streams") == 0) { ctx->batch_streams = value >= 2 ? 2 : 1; return VO_OK; }
+    if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
+    vo_set_error(ctx, "unknown option %s", key);
+    return VO_E_INVALID;
+}
+
 extern "C" long long vo_kernel_launches(const vo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset)

@@ -80,6 +80,7 @@ struct vo_ctx {
     int batch_units = 0;            // units configured by vo_batch_configure
     int batch_uploaded = 0;         // units currently resident
     bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
+    int batch_streams = 2;          // unit ranges run concurrently by the batched path
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
     cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
