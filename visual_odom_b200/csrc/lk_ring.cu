@@ -21,12 +21,20 @@
 //
 // Summation chains: OpenCV accumulates A11/A12/A22 and b1/b2 in float32 with 4 SIMD lanes over
 // columns 0..15 (lane = x & 3) and a scalar tail over columns 16..20, rows outermost.  The 441
-// window pixels are therefore split into 5 ordered chains (4 x 84 + 105 pixels).  Lanes 0..23
-// own the four SIMD chains (6 lanes x 14 consecutive chain elements), lanes 24..31 own the tail
-// (8 lanes x 14).  All addends are integers, so when the sum of |addend| over a chain is
-// <= 2^24 every partial sum is exact and the chain total is order independent: that fast path
-// uses integer shuffles.  Otherwise the chain is replayed faithfully: lane s adds its 14
-// elements in order and hands the running float to lane s+1.
+// window pixels are therefore split into 5 ordered chains (4 x 84 + 105 pixels); the addends of
+// b are float(int pair sum) of columns (x, x+4).
+//
+// Work mapping (who computes which pixel): COLUMN STRIPS.  Lane L owns window column L>>1, rows
+// 0..10 (L even) or 11..20 (L odd), plus up to 4 rows of one tail column (lanes 0..29).  A strip
+// walks down its column, so the two byte taps of a row are fetched once (two aligned 32-bit loads
+// + a funnel shift), serve as the bottom taps of one pixel and the top taps of the next, and feed
+// the fixed-point bilinear interpolation as packed operands of dp2a.
+//
+// Summation (who adds): all addends are integers, so when the sum of |addend| over every chain is
+// <= 2^24 each partial sum is exact and the chain totals are integer warp reductions (REDUX) --
+// the fast path.  Otherwise the float addends are written to shared memory in chain order and one
+// RUNNER lane per (quantity, chain) adds them strictly in order with 128-bit loads.  The A sums
+// always take the faithful path (they pass 2^24 on any corner-like texture).
 #include "common.cuh"
 #include "lk_ring.h"
 
@@ -138,14 +146,22 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
     w11 = (1 << W_BITS) - w00 - w01 - w10;
 }
 
-// tree reduction over the lanes of one chain group (6 or 8 consecutive lanes), result at sub==0
-__device__ __forceinline__ int group_sum(int v, int sub, int gsize)
+// a.lo * b.byte0 + a.hi * b.byte1 + c with SIGNED 16-bit halves of a (w11 = 2^14 - w00 - w01 - w10 can be -1)
+// and UNSIGNED bytes of b: the two horizontal taps of the fixed-point bilinear interpolation
+__device__ __forceinline__ int dp2a_taps(unsigned w_pair, unsigned taps, int c)
 {
-#pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        int o = __shfl_down_sync(FULL, v, d);
-        if (sub + d < gsize) v += o;
-    }
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w_pair), "r"(taps), "r"(c));
+    return d;
+}
+
+// sum over the 8 lanes of a SIMD chain: lanes that differ only in bit 0 (row half) and bits 3,4
+// (column group) -- every lane ends up with its own chain's total
+__device__ __forceinline__ unsigned chain_sum_u(unsigned v)
+{
+    v += __shfl_xor_sync(FULL, v, 1);
+    v += __shfl_xor_sync(FULL, v, 8);
+    v += __shfl_xor_sync(FULL, v, 16);
     return v;
 }
 
@@ -191,29 +207,28 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     const int npts = args.n_pts ? args.n_pts[unit] : args.cap;
     if (f >= npts) return;
 
-    // static lane -> chain-element assignment: lanes 0..23 = 4 SIMD chains x 6 lanes, 24..31 = tail
-    const bool tail = lane >= 24;
-    const int chain = tail ? 4 : lane / 6;
-    const int sub = tail ? lane - 24 : lane - chain * 6;
-    const int gsize = tail ? 8 : 6;
-    const int e0 = sub * 14;                       // first chain element of this lane
-    const int nel = tail ? (105 - e0 < 14 ? 105 - e0 : 14) : 14;   // elements owned (tail last lane: 7)
-    int woff[14];                                  // element k -> offset (row*IW + col) in a u8 box
-#pragma unroll
-    for (int k = 0; k < 14; k++) {
-        int e = e0 + k, row, col;
-        if (tail) { row = e / 5; col = 16 + e - row * 5; }
-        else { row = e >> 2; col = chain + 4 * (e & 3); }
-        if (k >= nel) { row = 0; col = 0; }
-        woff[k] = row * IW + col;
-    }
-    // chain-buffer slots: where this lane writes its addends, and (runner lanes) what it sums
-    // slot of (quantity q, chain c) = (5q + c) * CHS
-    const int a_slot = chain * CHS + sub * 14;                   // setup: 14 floats per lane and quantity
-    const int b_slot = chain * CHS + (tail ? sub * 14 : sub * 8);// iteration: 7 pairs (+1 zero) / 14 singles
+    // ---- static work mapping -------------------------------------------------------------------
+    const int col = lane >> 1, half = lane & 1;
+    const int r0 = half ? 11 : 0;                  // strip rows [r0, r0 + 11) (row 21 of the odd lanes is a dummy)
+    const int chain = col & 3, cpos = col >> 2;    // SIMD chain and position inside the row's group of 4
+    const bool has_tail = lane < 30;
+    const int tcol = has_tail ? 16 + lane / 6 : 16;
+    const int seg = lane % 6;
+    const int tr0 = has_tail ? (seg < 3 ? seg * 4 : 12 + (seg - 3) * 3) : 0;     // tail rows [tr0, tr0 + tn)
+    const int tn = has_tail ? (seg < 3 ? 4 : 3) : 0;
+    // chain-buffer positions (floats).  Slot of (quantity q, chain c) = (5q + c) * CHS.
+    //   A (setup)     : SIMD element (row, col) at row*4 + cpos ; tail element at row*5 + (tcol-16)
+    //   b (iteration) : SIMD pair (col, col+4) of a row at row*2 + cpos/2 (written by the even-cpos lane) ; tail as A
+    // Dummy elements (row 21 of odd lanes, unused tail rows, lanes 30/31) carry zero gradients: they
+    // write 0.0f exactly onto the zero padding the runner lanes read (positions 84.., 42..43, 105..111).
+    const int a_pos = chain * CHS + r0 * 4 + cpos;
+    const int b_pos = chain * CHS + r0 * 2 + (cpos >> 1);
+    const int t_pos = 4 * CHS + (has_tail ? tr0 * 5 + (tcol - 16) : 105 + (lane - 30) * 4);
+    const int t_stride = has_tail ? 5 : 1;
     const int rc = lane % 5;                                     // runner lane L sums slot L (quantity L/5, chain L%5)
-    const int a_base = lane * CHS, a_nvec = lane < 15 ? (rc < 4 ? 21 : 28) : 0;
-    const int b_base = lane * CHS, b_nvec = lane < 10 ? (rc < 4 ? 12 : 28) : 0;
+    const int a_nvec = lane < 15 ? (rc < 4 ? 21 : 28) : 0;
+    const int b_nvec = lane < 10 ? (rc < 4 ? 11 : 28) : 0;
+    const int run_base = lane * CHS;
 
     if (lane == 0) {
         mbar_init(&sm.bar, 1);
@@ -225,7 +240,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 
     const size_t pbase = (size_t)unit * args.cap + f;
     float2 pt = args.pts_in[pbase];
-    const float half = (VO_WIN - 1) * 0.5f;
+    const float half_win = (VO_WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
     const int max_level = args.nlevels - 1;
 
@@ -242,14 +257,14 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
             float px = pt.x * sc, py = pt.y * sc;
             if (level == max_level) { nxt.x = px; nxt.y = py; }
             else { nxt.x = nxt.x * 2.f; nxt.y = nxt.y * 2.f; }
-            px -= half; py -= half;
+            px -= half_win; py -= half_win;
             const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
             if (ipx < -VO_WIN || ipx >= lw || ipy < -VO_WIN || ipy >= lh) {
                 if (level == 0) { status = 0; errv = 0.f; }
                 continue;
             }
             // ---- stage windows: I (u8), dI (s16x2), J tile (u8) --------------------------------
-            float npx = nxt.x - half, npy = nxt.y - half;
+            float npx = nxt.x - half_win, npy = nxt.y - half_win;
             int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
             const bool j_ok0 = !(inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh);
             // box origins in padded-plane coordinates, x snapped down to the 16-byte boundary
@@ -272,8 +287,6 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     ldg_box_u8(sm.jtile, args.img_base[level] + args.plane[level] * img_next, args.pitch[level], jbx, jby, J_ROWS, lane);
                 __syncwarp();
             }
-            const uint8_t* ib = sm.iwin + (ipx + VO_PAD - ibx);
-            const uint32_t* db = sm.dwin + (ipx + VO_PAD - dbx);
             float a = px - (float)ipx, b = py - (float)ipy;
             int w00, w01, w10, w11;
             bilinear_weights(a, b, w00, w01, w10, w11);
@@ -284,33 +297,48 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 __syncwarp();
             }
 
-            // ---- patch extraction: I (x32), Ix, Iy for the 14 owned elements ------------------
-            int Ipk[7];           // two int16 patch intensities per register
-            int dxy[14];          // lo16 = Ix, hi16 = Iy
+            // ---- patch extraction: I (x32), Ix, Iy of the strip elements; A addends in chain order ----
+            int Ipk[8];           // int16 patch intensities, two per register: strip 0..10, tail 11..14
+            int dxy[15];          // lo16 = Ix, hi16 = Iy
             float A11, A12, A22;
             {
+                const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
+                const int ox = ipx + VO_PAD - ibx, odx = ipx + VO_PAD - dbx;
 #pragma unroll
-                for (int k = 0; k < 14; k++) {
-                    const uint8_t* s0 = ib + woff[k];
-                    const int ival = (s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5);
-                    const int row = woff[k] / IW, col = woff[k] - row * IW;
-                    const uint32_t* d0 = db + row * DW + col;
-                    const uint32_t d00 = d0[0], d01 = d0[1], d10 = d0[DW], d11 = d0[DW + 1];
-                    int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
-                              (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    int iy = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 +
-                              ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    if (k >= nel) { ix = 0; iy = 0; }
-                    if (k & 1) Ipk[k >> 1] |= ival << 16; else Ipk[k >> 1] = ival & 0xffff;
-                    dxy[k] = (ix & 0xffff) | (iy << 16);
-                    const float fx = (float)ix, fy = (float)iy;
-                    // chain-ordered addends of A11 / A12 / A22 (zero for the unused tail slots)
-                    sm.chain[0 * 5 * CHS + a_slot + k] = __fmul_rn(fx, fx);
-                    sm.chain[1 * 5 * CHS + a_slot + k] = __fmul_rn(fx, fy);
-                    sm.chain[2 * 5 * CHS + a_slot + k] = __fmul_rn(fy, fy);
+                for (int part = 0; part < 2; part++) {
+                    const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11, nvalid = part ? tn : (half ? 10 : 11);
+                    const uint8_t* ib = sm.iwin + row0 * IW + ox + c0;
+                    const uint32_t* iw = reinterpret_cast<const uint32_t*>((uintptr_t)ib & ~(uintptr_t)3);
+                    const int ish = 8 * (int)((uintptr_t)ib & 3);
+                    const uint32_t* dw = sm.dwin + row0 * DW + odx + c0;
+                    unsigned ptop = __funnelshift_r(iw[0], iw[1], ish);
+                    unsigned d00 = dw[0], d01 = dw[1];
+#pragma unroll
+                    for (int k = 0; k < ne; k++) {
+                        const unsigned pbot = __funnelshift_r(iw[(k + 1) * (IW / 4)], iw[(k + 1) * (IW / 4) + 1], ish);
+                        const unsigned d10 = dw[(k + 1) * DW], d11 = dw[(k + 1) * DW + 1];
+                        const int ival = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5));
+                        int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
+                                  (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                        int iy = (((int)d00 >> 16) * w00 + ((int)d01 >> 16) * w01 +
+                                  ((int)d10 >> 16) * w10 + ((int)d11 >> 16) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                        if (k >= nvalid) { ix = 0; iy = 0; }
+                        const int e = part ? 11 + k : k;
+                        if (e & 1) Ipk[e >> 1] |= ival << 16; else Ipk[e >> 1] = ival & 0xffff;
+                        dxy[e] = (ix & 0xffff) | (iy << 16);
+                        const float fx = (float)ix, fy = (float)iy;
+                        const int pos = part ? t_pos + k * t_stride : a_pos + k * 4;
+                        // an unused tail row of a 3-row segment is the first row of the next lane's segment: no store
+                        if (!part || k < tn || !has_tail) {
+                            sm.chain[0 * 5 * CHS + pos] = __fmul_rn(fx, fx);
+                            sm.chain[1 * 5 * CHS + pos] = __fmul_rn(fx, fy);
+                            sm.chain[2 * 5 * CHS + pos] = __fmul_rn(fy, fy);
+                        }
+                        ptop = pbot; d00 = d10; d01 = d11;
+                    }
                 }
                 __syncwarp();
-                const float acc = run_chain(sm.chain, a_base, a_nvec);
+                const float acc = run_chain(sm.chain, run_base, a_nvec);
                 const float iA11 = combine_chains(acc, 0), iA12 = combine_chains(acc, 1), iA22 = combine_chains(acc, 2);
                 A11 = __fmul_rn(iA11, FLT_SCALE); A12 = __fmul_rn(iA12, FLT_SCALE); A22 = __fmul_rn(iA22, FLT_SCALE);
                 __syncwarp();
@@ -357,59 +385,68 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 }
                 a = npx - (float)inx; b = npy - (float)iny;
                 bilinear_weights(a, b, w00, w01, w10, w11);
-                const uint8_t* jb = sm.jtile + ry * IW + rx;
-                int dpk[7];                       // two int16 residuals per register
-                int sx = 0, sy = 0;
-                unsigned ax = 0, ay = 0;
+                const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
+                int dpk[8];                       // int16 residuals, two per register (same element order as Ipk)
+                int sxs = 0, sys = 0, sxt = 0, syt = 0;         // signed sums: strip (my SIMD chain) / tail
+                unsigned axs = 0, ays = 0, axt = 0, ayt = 0;    // sums of |addend|
 #pragma unroll
-                for (int k = 0; k < 14; k++) {
-                    const uint8_t* s0 = jb + woff[k];
-                    const int Iv = (k & 1) ? (Ipk[k >> 1] >> 16) : (int)(short)(Ipk[k >> 1] & 0xffff);
-                    const int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
-                    if (k & 1) dpk[k >> 1] |= diff << 16; else dpk[k >> 1] = diff & 0xffff;
-                    const int vx = diff * (int)(short)(dxy[k] & 0xffff);      // Ix, Iy are 0 for unused slots
-                    const int vy = diff * (dxy[k] >> 16);
-                    sx += vx; sy += vy;
-                    ax += (unsigned)abs(vx); ay += (unsigned)abs(vy);
+                for (int part = 0; part < 2; part++) {
+                    const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11;
+                    const uint8_t* jb = sm.jtile + (ry + row0) * IW + rx + c0;
+                    const uint32_t* jw = reinterpret_cast<const uint32_t*>((uintptr_t)jb & ~(uintptr_t)3);
+                    const int jsh = 8 * (int)((uintptr_t)jb & 3);
+                    unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
+#pragma unroll
+                    for (int k = 0; k < ne; k++) {
+                        const unsigned pbot = __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh);
+                        const int e = part ? 11 + k : k;
+                        const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
+                        const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
+                        if (e & 1) dpk[e >> 1] |= diff << 16; else dpk[e >> 1] = diff & 0xffff;
+                        const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
+                        const int vy = diff * (dxy[e] >> 16);
+                        if (part) { sxt += vx; syt += vy; axt += (unsigned)abs(vx); ayt += (unsigned)abs(vy); }
+                        else { sxs += vx; sys += vy; axs += (unsigned)abs(vx); ays += (unsigned)abs(vy); }
+                        ptop = pbot;
+                    }
                 }
-                // per-chain totals (exact integers) and per-chain sum of |addend|
-                const int csx = group_sum(sx, sub, gsize), csy = group_sum(sy, sub, gsize);
-                const int cax = group_sum((int)ax, sub, gsize), cay = group_sum((int)ay, sub, gsize);
-                // |pair sum| <= |v0|+|v1|, so the bound is conservative for the SIMD chains
-                const bool exact = __all_sync(FULL, (sub != 0) || ((unsigned)cax <= (1u << 24) && (unsigned)cay <= (1u << 24)));
+                // per-chain totals (exact integers) and per-chain sums of |addend| (REDUX over the chain's lanes)
+                const unsigned cax = chain_sum_u(axs), cay = chain_sum_u(ays);
+                const unsigned tax = __reduce_add_sync(FULL, axt), tay = __reduce_add_sync(FULL, ayt);
+                // |pair sum| <= |v0| + |v1|, so the bound is conservative for the SIMD chains
+                const bool exact = __all_sync(FULL, cax <= (1u << 24) && cay <= (1u << 24) && tax <= (1u << 24) && tay <= (1u << 24));
                 float ib1, ib2;
                 if (exact) {
-                    // every partial sum of every chain is an exactly representable integer:
-                    // chain totals live in lanes 0, 6, 12, 18 (SIMD) and 24 (tail)
-                    const float fx = (float)csx, fy = (float)csy;
-                    float c0 = __shfl_sync(FULL, fx, 0), c1 = __shfl_sync(FULL, fx, 6), c2 = __shfl_sync(FULL, fx, 12),
-                          c3 = __shfl_sync(FULL, fx, 18), t = __shfl_sync(FULL, fx, 24);
-                    ib1 = __fadd_rn(t, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
-                    c0 = __shfl_sync(FULL, fy, 0); c1 = __shfl_sync(FULL, fy, 6); c2 = __shfl_sync(FULL, fy, 12);
-                    c3 = __shfl_sync(FULL, fy, 18); t = __shfl_sync(FULL, fy, 24);
-                    ib2 = __fadd_rn(t, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
+                    // every partial sum of every chain is an exactly representable integer
+                    const float fx = (float)(int)chain_sum_u((unsigned)sxs), fy = (float)(int)chain_sum_u((unsigned)sys);
+                    const float tx = (float)__reduce_add_sync(FULL, sxt), ty = (float)__reduce_add_sync(FULL, syt);
+                    float c0 = __shfl_sync(FULL, fx, 0), c1 = __shfl_sync(FULL, fx, 2), c2 = __shfl_sync(FULL, fx, 4), c3 = __shfl_sync(FULL, fx, 6);
+                    ib1 = __fadd_rn(tx, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
+                    c0 = __shfl_sync(FULL, fy, 0); c1 = __shfl_sync(FULL, fy, 2); c2 = __shfl_sync(FULL, fy, 4); c3 = __shfl_sync(FULL, fy, 6);
+                    ib2 = __fadd_rn(ty, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
                 } else {
-                    // faithful replay: write the float addends in chain order, runner lanes add them
-                    float* cx = sm.chain + b_slot;
-                    float* cy = sm.chain + 5 * CHS + b_slot;
-                    if (!tail) {
+                    // faithful replay: float addends in chain order, runner lanes add them
 #pragma unroll
-                        for (int k = 0; k < 7; k++) {
-                            const int d0 = (int)(short)(dpk[k] & 0xffff), d1 = dpk[k] >> 16;
-                            cx[k] = (float)(d0 * (int)(short)(dxy[2 * k] & 0xffff) + d1 * (int)(short)(dxy[2 * k + 1] & 0xffff));
-                            cy[k] = (float)(d0 * (dxy[2 * k] >> 16) + d1 * (dxy[2 * k + 1] >> 16));
+                    for (int k = 0; k < 11; k++) {
+                        const int d = (k & 1) ? (dpk[k >> 1] >> 16) : (int)(short)(dpk[k >> 1] & 0xffff);
+                        const int vx = d * (int)(short)(dxy[k] & 0xffff), vy = d * (dxy[k] >> 16);
+                        const int px2 = vx + __shfl_down_sync(FULL, vx, 8), py2 = vy + __shfl_down_sync(FULL, vy, 8);   // + column x+4
+                        if (!(cpos & 1)) {
+                            sm.chain[b_pos + k * 2] = (float)px2;
+                            sm.chain[5 * CHS + b_pos + k * 2] = (float)py2;
                         }
-                        cx[7] = 0.f; cy[7] = 0.f;
-                    } else {
+                    }
 #pragma unroll
-                        for (int k = 0; k < 14; k++) {
-                            const int d = (k & 1) ? (dpk[k >> 1] >> 16) : (int)(short)(dpk[k >> 1] & 0xffff);
-                            cx[k] = (float)(d * (int)(short)(dxy[k] & 0xffff));
-                            cy[k] = (float)(d * (dxy[k] >> 16));
+                    for (int k = 0; k < 4; k++) {
+                        const int e = 11 + k;
+                        const int d = (e & 1) ? (dpk[e >> 1] >> 16) : (int)(short)(dpk[e >> 1] & 0xffff);
+                        if (k < tn || !has_tail) {
+                            sm.chain[t_pos + k * t_stride] = (float)(d * (int)(short)(dxy[e] & 0xffff));
+                            sm.chain[5 * CHS + t_pos + k * t_stride] = (float)(d * (dxy[e] >> 16));
                         }
                     }
                     __syncwarp();
-                    const float acc = run_chain(sm.chain, b_base, b_nvec);
+                    const float acc = run_chain(sm.chain, run_base, b_nvec);
                     ib1 = combine_chains(acc, 0);
                     ib2 = combine_chains(acc, 1);
                     __syncwarp();
@@ -418,7 +455,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
                 const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
                 npx = __fadd_rn(npx, dx); npy = __fadd_rn(npy, dy);
-                nxt.x = __fadd_rn(npx, half); nxt.y = __fadd_rn(npy, half);
+                nxt.x = __fadd_rn(npx, half_win); nxt.y = __fadd_rn(npy, half_win);
                 if ((double)dx * (double)dx + (double)dy * (double)dy <= args.eps2) break;
                 if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
                     nxt.x = __fsub_rn(nxt.x, __fmul_rn(dx, 0.5f));
@@ -430,7 +467,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 
             // ---- level 0 epilogue: final bounds re-check (+ err when requested) ---------------
             if (level == 0 && status) {
-                float fxp = __fsub_rn(nxt.x, half), fyp = __fsub_rn(nxt.y, half);
+                float fxp = __fsub_rn(nxt.x, half_win), fyp = __fsub_rn(nxt.y, half_win);
                 inx = __float2int_rd(fxp); iny = __float2int_rd(fyp);
                 if (inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh) {
                     status = 0;
@@ -455,19 +492,28 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     }
                     a = fxp - (float)inx; b = fyp - (float)iny;
                     bilinear_weights(a, b, w00, w01, w10, w11);
-                    const uint8_t* jb = sm.jtile + ry * IW + rx;
+                    const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
                     // errval += |diff| is a plain row-major float sum of small integers
                     // (<= 441 * 8160 < 2^24): exact, so any order gives the same float.
                     int s = 0;
 #pragma unroll
-                    for (int k = 0; k < 14; k++) {
-                        const uint8_t* s0 = jb + woff[k];
-                        const int Iv = (k & 1) ? (Ipk[k >> 1] >> 16) : (int)(short)(Ipk[k >> 1] & 0xffff);
-                        const int diff = ((s0[0] * w00 + s0[1] * w01 + s0[IW] * w10 + s0[IW + 1] * w11 + (1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
-                        if (k < nel) s += abs(diff);
-                    }
+                    for (int part = 0; part < 2; part++) {
+                        const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11, nvalid = part ? tn : (half ? 10 : 11);
+                        const uint8_t* jb = sm.jtile + (ry + row0) * IW + rx + c0;
+                        const uint32_t* jw = reinterpret_cast<const uint32_t*>((uintptr_t)jb & ~(uintptr_t)3);
+                        const int jsh = 8 * (int)((uintptr_t)jb & 3);
+                        unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULL, s, d);
+                        for (int k = 0; k < ne; k++) {
+                            const unsigned pbot = __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh);
+                            const int e = part ? 11 + k : k;
+                            const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
+                            const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
+                            if (k < nvalid) s += abs(diff);
+                            ptop = pbot;
+                        }
+                    }
+                    s = __reduce_add_sync(FULL, s);
                     errv = __fdiv_rn(__fmul_rn((float)s, 1.f), (float)(32 * VO_WIN * VO_WIN));
                 }
             }
