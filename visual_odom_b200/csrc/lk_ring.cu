@@ -307,9 +307,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 #pragma unroll
                 for (int part = 0; part < 2; part++) {
                     const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11, nvalid = part ? tn : (half ? 10 : 11);
-                    const uint8_t* ib = sm.iwin + row0 * IW + ox + c0;
-                    const uint32_t* iw = reinterpret_cast<const uint32_t*>((uintptr_t)ib & ~(uintptr_t)3);
-                    const int ish = 8 * (int)((uintptr_t)ib & 3);
+                    const int ioff = row0 * IW + ox + c0;                      // byte offset of the strip's first tap
+                    const uint32_t* iw = reinterpret_cast<const uint32_t*>(sm.iwin) + (ioff >> 2);
+                    const int ish = 8 * (ioff & 3);
                     const uint32_t* dw = sm.dwin + row0 * DW + odx + c0;
                     unsigned ptop = __funnelshift_r(iw[0], iw[1], ish);
                     unsigned d00 = dw[0], d01 = dw[1];
@@ -392,9 +392,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 #pragma unroll
                 for (int part = 0; part < 2; part++) {
                     const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11;
-                    const uint8_t* jb = sm.jtile + (ry + row0) * IW + rx + c0;
-                    const uint32_t* jw = reinterpret_cast<const uint32_t*>((uintptr_t)jb & ~(uintptr_t)3);
-                    const int jsh = 8 * (int)((uintptr_t)jb & 3);
+                    const int joff = (ry + row0) * IW + rx + c0;
+                    const uint32_t* jw = reinterpret_cast<const uint32_t*>(sm.jtile) + (joff >> 2);
+                    const int jsh = 8 * (joff & 3);
                     unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
 #pragma unroll
                     for (int k = 0; k < ne; k++) {
@@ -499,9 +499,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 #pragma unroll
                     for (int part = 0; part < 2; part++) {
                         const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11, nvalid = part ? tn : (half ? 10 : 11);
-                        const uint8_t* jb = sm.jtile + (ry + row0) * IW + rx + c0;
-                        const uint32_t* jw = reinterpret_cast<const uint32_t*>((uintptr_t)jb & ~(uintptr_t)3);
-                        const int jsh = 8 * (int)((uintptr_t)jb & 3);
+                        const int joff = (ry + row0) * IW + rx + c0;
+                        const uint32_t* jw = reinterpret_cast<const uint32_t*>(sm.jtile) + (joff >> 2);
+                        const int jsh = 8 * (joff & 3);
                         unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
 #pragma unroll
                         for (int k = 0; k < ne; k++) {
