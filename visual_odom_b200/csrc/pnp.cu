@@ -83,25 +83,150 @@ __global__ void k_pnp_subsets(const PnpArgs a, int it0, int it1)
     s.rng_state = rng.state;
 }
 
-__global__ void __launch_bounds__(32) k_pnp_hypotheses(const PnpArgs a, int it0, int it1)
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative one-sided Jacobi SVD of the symmetric 12x12 Gram matrix (U^T and W only).
+// Lane r (< 12) of a 16-lane group owns row r of At in registers.  OpenCV sweeps the pairs (i, j) in
+// row-major order; a pair only depends on earlier pairs that touch row i or row j, and all of those
+// have a smaller i + j, so the pairs of one anti-diagonal (i + j = t) are independent: the sweep is
+// run as 21 wavefronts of up to 6 disjoint pairs, each pair on its two row-owner lanes, with exactly
+// the operations (and operation order) of jacobi_svd_t -- the result is bit-identical, 3x shorter.
+// Returns false when a singular value is exactly zero (the caller then uses the sequential routine,
+// which implements OpenCV's random-vector completion for that case).
+__device__ bool jacobi12_coop(double (&row)[12], double& wout, int r, int gbase, unsigned gmask)
+{
+    const double eps = kDblEps * 10;
+    const bool live = r < 12;
+    double W = 0;
+    for (int k = 0; k < 12; k++) W += row[k] * row[k];
+    for (int iter = 0; iter < 30; iter++) {
+        bool changed = false;
+        for (int t = 1; t <= 21; t++) {
+            const int partner = t - r;
+            const bool active = live && partner >= 0 && partner < 12 && partner != r;
+            const int src = gbase + (active ? partner : r);
+            double other[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) other[k] = __shfl_sync(gmask, row[k], src);
+            const double Wo = __shfl_sync(gmask, W, src);
+            if (active) {
+                const bool is_i = r < partner;
+                const double a0 = is_i ? W : Wo, b0 = is_i ? Wo : W;
+                double p = 0;
+#pragma unroll
+                for (int k = 0; k < 12; k++) p += row[k] * other[k];          // Ai[k]*Aj[k]: the product commutes
+                if (!(fabs(p) <= eps * sqrt(a0 * b0))) {
+                    p *= 2;
+                    const double beta = a0 - b0, gamma = cv_hypot(p, beta);
+                    double c, s;
+                    if (beta < 0) {
+                        const double delta = (gamma - beta) * 0.5;
+                        s = sqrt(delta / gamma);
+                        c = p / (gamma * s * 2);
+                    } else {
+                        c = sqrt((gamma + beta) / (gamma * 2));
+                        s = p / (gamma * c * 2);
+                    }
+                    double acc = 0;
+                    if (is_i) {
+#pragma unroll
+                        for (int k = 0; k < 12; k++) { const double t0 = c * row[k] + s * other[k]; row[k] = t0; acc += t0 * t0; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 12; k++) { const double t1 = -s * other[k] + c * row[k]; row[k] = t1; acc += t1 * t1; }
+                    }
+                    W = acc;
+                    changed = true;
+                }
+            }
+        }
+        if (!__any_sync(gmask, changed)) break;
+    }
+    double sd = 0;
+    for (int k = 0; k < 12; k++) sd += row[k] * row[k];
+    W = sqrt(sd);
+    wout = W;
+    return !__any_sync(gmask, live && W <= kDblMin);
+}
+
+// One iteration (hypothesis) per 16-lane group: the leader lane runs the scalar stages of EPnP
+// (pnp_math.cuh), the 12 row-owner lanes run the SVD of the Gram matrix.
+#define HYP_PER_CTA 2
+__global__ void __launch_bounds__(32 * 1) k_pnp_hypotheses(const PnpArgs a, int it0, int it1)
 {
     const int unit = blockIdx.y;
-    const int it = it0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, g = lane >> 4, r = lane & 15;
+    const int it = it0 + blockIdx.x * HYP_PER_CTA + g;
     const PnpState& s = a.state[unit];
-    if (s.done || it >= it1 || it >= s.niters) return;
-    const int* idx = a.subsets + ((size_t)unit * a.iterations + it) * 5;
-    float Xs[15], xs[10];
-    for (int i = 0; i < 5; i++) {
-        const float3 P = a.X[(size_t)unit * a.cap + idx[i]];
-        const float2 p = a.x[(size_t)unit * a.cap + idx[i]];
-        Xs[3 * i] = P.x; Xs[3 * i + 1] = P.y; Xs[3 * i + 2] = P.z;
-        xs[2 * i] = p.x; xs[2 * i + 1] = p.y;
+    const bool work = !(s.done || it >= it1 || it >= s.niters);
+    const unsigned gmask = 0xffffu << (16 * g);
+    if (!__any_sync(0xffffffffu, work)) return;
+    __shared__ double sm_mtm[HYP_PER_CTA][144];
+    __shared__ double sm_ut[HYP_PER_CTA][48];        // rows 11, 10, 9, 8 of U^T
+    __shared__ int sm_rank_ok[HYP_PER_CTA];
+    Epnp5State st;
+    if (work && r == 0) {
+        const int* idx = a.subsets + ((size_t)unit * a.iterations + it) * 5;
+        float Xs[15], xs[10];
+        for (int i = 0; i < 5; i++) {
+            const float3 P = a.X[(size_t)unit * a.cap + idx[i]];
+            const float2 p = a.x[(size_t)unit * a.cap + idx[i]];
+            Xs[3 * i] = P.x; Xs[3 * i + 1] = P.y; Xs[3 * i + 2] = P.z;
+            xs[2 * i] = p.x; xs[2 * i + 1] = p.y;
+        }
+        epnp5_front(Xs, xs, a.fu, a.fv, a.uc, a.vc, st, sm_mtm[g]);
     }
-    double rvec[3], tvec[3], R[9];
-    epnp5(Xs, xs, a.fu, a.fv, a.uc, a.vc, rvec, tvec, R);
-    double* m = a.models + ((size_t)unit * a.iterations + it) * 12;
-    for (int k = 0; k < 9; k++) m[k] = R[k];
-    for (int k = 0; k < 3; k++) m[9 + k] = tvec[k];
+    __syncwarp();
+    if (work) {          // uniform per 16-lane group
+        double row[12], W;
+#pragma unroll
+        for (int k = 0; k < 12; k++) row[k] = (r < 12) ? sm_mtm[g][r * 12 + k] : 0.0;
+        const bool ok = jacobi12_coop(row, W, r, 16 * g, gmask);
+        // OpenCV then orders the rows by descending W with a selection sort (first maximum wins, swap);
+        // every lane replays it on the 12 values to learn which original row lands at positions 8..11
+        double Wv[12];
+        int id[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) { Wv[k] = __shfl_sync(gmask, W, 16 * g + k); id[k] = k; }
+#pragma unroll
+        for (int i = 0; i < 11; i++) {
+            int best = i, bid = id[i];
+            double bv = Wv[i];
+#pragma unroll
+            for (int k = i + 1; k < 12; k++)
+                if (bv < Wv[k]) { bv = Wv[k]; best = k; bid = id[k]; }
+            const double wi = Wv[i];
+            const int ii = id[i];
+#pragma unroll
+            for (int k = i + 1; k < 12; k++)
+                if (k == best) { Wv[k] = wi; id[k] = ii; }
+            Wv[i] = bv; id[i] = bid;
+        }
+        if (r < 12) {
+            const double sc = W > kDblMin ? 1 / W : 0.;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (id[11 - q] == r) {
+#pragma unroll
+                    for (int k = 0; k < 12; k++) sm_ut[g][q * 12 + k] = row[k] * sc;
+                }
+        }
+        if (r == 0) sm_rank_ok[g] = ok ? 1 : 0;
+    }
+    __syncwarp();
+    if (work && r == 0) {
+        double rvec[3], tvec[3], R[9];
+        if (sm_rank_ok[g]) {
+            epnp5_back(st, sm_ut[g], sm_ut[g] + 12, sm_ut[g] + 24, sm_ut[g] + 36, rvec, tvec, R);
+        } else {        // exactly-zero singular value: the sequential routine handles OpenCV's completion rule
+            double ut[144], W12[12];
+            for (int k = 0; k < 144; k++) ut[k] = sm_mtm[g][k];
+            jacobi_svd_t<12, 12, false>(ut, W12, nullptr, 12);
+            epnp5_back(st, ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8, rvec, tvec, R);
+        }
+        double* m = a.models + ((size_t)unit * a.iterations + it) * 12;
+        for (int k = 0; k < 9; k++) m[k] = R[k];
+        for (int k = 0; k < 3; k++) m[9 + k] = tvec[k];
+    }
 }
 
 __device__ __forceinline__ float reproj_err(const double* m, float3 P, float2 p, double fu, double fv, double uc, double vc)
@@ -427,7 +552,7 @@ int vo_launch_pnp(const PnpArgs& a, cudaStream_t stream)
         if (it1 > a.iterations) it1 = a.iterations;
         if (it0 >= it1) continue;
         k_pnp_subsets<<<ub, 64, 0, stream>>>(a, it0, it1);
-        dim3 gh((it1 - it0 + 31) / 32, a.n_units);
+        dim3 gh((it1 - it0 + 1) / 2, a.n_units);          // two hypotheses (16-lane groups) per warp
         k_pnp_hypotheses<<<gh, 32, 0, stream>>>(a, it0, it1);
         dim3 gc(it1 - it0, a.n_units);
         k_pnp_count<<<gc, 128, 0, stream>>>(a, it0, it1);

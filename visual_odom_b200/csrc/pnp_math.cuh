@@ -47,7 +47,9 @@ VO_HD double cv_hypot(double a, double b)
 
 // JacobiSVDImpl_<double>: At is N rows x M (= A^T, row stride M), on exit rows of At are U^T
 // (first n1 rows normalised), W singular values (descending), Vt N x N.
-template <int M, int N>
+// WANT_V = false skips the accumulation of V (it never feeds back into At / W, so U^T and W are
+// bit-identical either way); Vt may then be nullptr.
+template <int M, int N, bool WANT_V = true>
 VO_HDN void jacobi_svd_t(double* At, double* W, double* Vt, int n1)
 {
     const double eps = kDblEps * 10;
@@ -55,8 +57,10 @@ VO_HDN void jacobi_svd_t(double* At, double* W, double* Vt, int n1)
         double sd = 0;
         for (int k = 0; k < M; k++) { double t = At[i * M + k]; sd += t * t; }
         W[i] = sd;
-        for (int k = 0; k < N; k++) Vt[i * N + k] = 0;
-        Vt[i * N + i] = 1;
+        if (WANT_V) {
+            for (int k = 0; k < N; k++) Vt[i * N + k] = 0;
+            Vt[i * N + i] = 1;
+        }
     }
     const int max_iter = M > 30 ? M : 30;
     for (int iter = 0; iter < max_iter; iter++) {
@@ -86,11 +90,13 @@ VO_HDN void jacobi_svd_t(double* At, double* W, double* Vt, int n1)
                 }
                 W[i] = a; W[j] = b;
                 changed = true;
-                double* Vi = Vt + i * N; double* Vj = Vt + j * N;
-                for (int k = 0; k < N; k++) {
-                    double t0 = c * Vi[k] + s * Vj[k];
-                    double t1 = -s * Vi[k] + c * Vj[k];
-                    Vi[k] = t0; Vj[k] = t1;
+                if (WANT_V) {
+                    double* Vi = Vt + i * N; double* Vj = Vt + j * N;
+                    for (int k = 0; k < N; k++) {
+                        double t0 = c * Vi[k] + s * Vj[k];
+                        double t1 = -s * Vi[k] + c * Vj[k];
+                        Vi[k] = t0; Vj[k] = t1;
+                    }
                 }
             }
         if (!changed) break;
@@ -107,7 +113,7 @@ VO_HDN void jacobi_svd_t(double* At, double* W, double* Vt, int n1)
         if (i != j) {
             double t = W[i]; W[i] = W[j]; W[j] = t;
             for (int k = 0; k < M; k++) { t = At[i * M + k]; At[i * M + k] = At[j * M + k]; At[j * M + k] = t; }
-            for (int k = 0; k < N; k++) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+            if (WANT_V) for (int k = 0; k < N; k++) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
         }
     }
     Rng rng(0x12345678);
@@ -300,14 +306,23 @@ VO_HDN inline bool qr_solve_6x4(double* A, double* b, double* X)
     return true;
 }
 
-// cv::solvePnP(..., SOLVEPNP_EPNP) on exactly 5 correspondences, zero distortion.
+// cv::solvePnP(..., SOLVEPNP_EPNP) on exactly 5 correspondences, zero distortion, in three stages so
+// that the middle one (the 12x12 Jacobi SVD, 3/4 of the work) can be replaced by the warp-cooperative
+// version in pnp.cu:  epnp5_front -> M^T M ;  SVD ;  epnp5_back(left singular vectors 11, 10, 9, 8).
 //   Xw[5][3] object points (float inputs widened to double), uv[5][2] pixel coordinates (float),
 //   fu, fv, uc, vc intrinsics (float values widened to double).  Out: rvec[3], tvec[3], R[9].
-VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double fv, double uc, double vc,
-                         double* rvec, double* tvec, double* Rout)
+struct Epnp5State {
+    double X[5][3], us[5][2], cws[4][3], al[5][4];
+    double fu, fv, uc, vc;
+};
+
+VO_HDN inline void epnp5_front(const float* Xw_f, const float* uv_f, double fu, double fv, double uc, double vc,
+                               Epnp5State& st, double* MtM /* 144, symmetric */)
 {
+    st.fu = fu; st.fv = fv; st.uc = uc; st.vc = vc;
+
     const int n = 5;
-    double X[5][3], us[5][2];
+    double (&X)[5][3] = st.X; double (&us)[5][2] = st.us;
     for (int i = 0; i < n; i++) {
         for (int j = 0; j < 3; j++) X[i][j] = (double)Xw_f[3 * i + j];
         // undistortPoints (zero distortion): normalised coordinate in f64, STORED AS FLOAT
@@ -318,13 +333,13 @@ VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double
         us[i][1] = (double)yn * fv + vc;
     }
     // choose_control_points
-    double cws[4][3];
+    double (&cws)[4][3] = st.cws;
     for (int j = 0; j < 3; j++) cws[0][j] = 0;
     for (int i = 0; i < n; i++)
         for (int j = 0; j < 3; j++) cws[0][j] += X[i][j];
     for (int j = 0; j < 3; j++) cws[0][j] /= n;
     {
-        double pw0[5][3], G[9], dc[3], At[9], Vt[9];
+        double pw0[5][3], G[9], dc[3], At[9];
         for (int i = 0; i < n; i++)
             for (int j = 0; j < 3; j++) pw0[i][j] = X[i][j] - cws[0][j];
         for (int i = 0; i < 3; i++)
@@ -335,14 +350,14 @@ VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double
             }
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++) At[j * 3 + i] = G[i * 3 + j];
-        jacobi_svd_t<3, 3>(At, dc, Vt, 3);         // rows of At = U^T = uct
+        jacobi_svd_t<3, 3, false>(At, dc, nullptr, 3);         // rows of At = U^T = uct (V is not needed)
         for (int i = 1; i < 4; i++) {
             const double k = sqrt(dc[i - 1] / n);
             for (int j = 0; j < 3; j++) cws[i][j] = cws[0][j] + k * At[(i - 1) * 3 + j];
         }
     }
     // compute_barycentric_coordinates
-    double al[5][4];
+    double (&al)[5][4] = st.al;
     {
         double cc[9], ci[9];
         for (int i = 0; i < 3; i++)
@@ -355,28 +370,33 @@ VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double
             al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
         }
     }
-    // M (10 x 12), M^T M, its left singular vectors
-    double ut[144];
-    {
-        double M[10 * 12];
-        for (int k = 0; k < 120; k++) M[k] = 0;
-        for (int i = 0; i < n; i++)
-            for (int j = 0; j < 4; j++) {
-                M[(2 * i) * 12 + 3 * j] = al[i][j] * fu;
-                M[(2 * i) * 12 + 3 * j + 2] = al[i][j] * (uc - us[i][0]);
-                M[(2 * i + 1) * 12 + 3 * j + 1] = al[i][j] * fv;
-                M[(2 * i + 1) * 12 + 3 * j + 2] = al[i][j] * (vc - us[i][1]);
-            }
-        double W[12], Vt[144];
-        for (int i = 0; i < 12; i++)
-            for (int j = i; j < 12; j++) {
-                double s = 0;
-                for (int k = 0; k < 10; k++) s += M[k * 12 + i] * M[k * 12 + j];
-                ut[i * 12 + j] = s; ut[j * 12 + i] = s;     // symmetric: A^T == A
-            }
-        jacobi_svd_t<12, 12>(ut, W, Vt, 12);               // rows of ut are now U^T
-    }
-    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+    // M (10 x 12) and its Gram matrix (cv::mulTransposed: sequential sums over the rows)
+    double M[10 * 12];
+    for (int k = 0; k < 120; k++) M[k] = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 4; j++) {
+            M[(2 * i) * 12 + 3 * j] = al[i][j] * fu;
+            M[(2 * i) * 12 + 3 * j + 2] = al[i][j] * (uc - us[i][0]);
+            M[(2 * i + 1) * 12 + 3 * j + 1] = al[i][j] * fv;
+            M[(2 * i + 1) * 12 + 3 * j + 2] = al[i][j] * (vc - us[i][1]);
+        }
+    for (int i = 0; i < 12; i++)
+        for (int j = i; j < 12; j++) {
+            double s = 0;
+            for (int k = 0; k < 10; k++) s += M[k * 12 + i] * M[k * 12 + j];
+            MtM[i * 12 + j] = s; MtM[j * 12 + i] = s;
+        }
+}
+
+// v0..v3: rows 11, 10, 9, 8 of U^T of the SVD of M^T M (12 doubles each)
+VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const double* v1, const double* v2, const double* v3,
+                              double* rvec, double* tvec, double* Rout)
+{
+    const int n = 5;
+    const double (&X)[5][3] = st.X; const double (&us)[5][2] = st.us;
+    const double (&cws)[4][3] = st.cws; const double (&al)[5][4] = st.al;
+    const double fu = st.fu, fv = st.fv, uc = st.uc, vc = st.vc;
+    const double* v[4] = {v0, v1, v2, v3};
     double L[6][10], rho[6];
     {
         double dv[4][6][3];
@@ -513,6 +533,17 @@ VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double
     for (int k = 0; k < 3; k++) tvec[k] = best_t[k];
     // PnPRansacCallback::computeError -> projectPoints(rvec) converts back with Rodrigues
     rodrigues_fwd(rvec, Rout);
+}
+
+
+VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double fv, double uc, double vc,
+                         double* rvec, double* tvec, double* Rout)
+{
+    Epnp5State st;
+    double ut[144], W[12];
+    epnp5_front(Xw_f, uv_f, fu, fv, uc, vc, st, ut);                 // symmetric: A^T == A
+    jacobi_svd_t<12, 12, false>(ut, W, nullptr, 12);                 // rows of ut are now U^T (V is not needed)
+    epnp5_back(st, ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8, rvec, tvec, Rout);
 }
 
 // per-point DLT of cv::triangulatePoints: X4 = last row of V^T of the 4x4 system (stored float),
