@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--units", type=int, default=8, help="independent stereo pairs per step per GPU")
     ap.add_argument("--features", type=int, default=N_FEAT)
     ap.add_argument("--cpu-sample", type=int, default=12, help="frames timed for cpu_baseline")
+    ap.add_argument("--width", type=int, default=W_IMG)
+    ap.add_argument("--height", type=int, default=H_IMG)
+    ap.add_argument("--calib", default="kitti", choices=["kitti", "zed"], help="intrinsics of the synthetic rig")
     return ap.parse_args()
 
 
@@ -64,7 +67,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -134,7 +137,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from visual_odom_b200 import synth
-    units = [synth.stereo_unit(W_IMG, H_IMG, s) for s in range(args.units)]
+    global W_IMG, H_IMG
+    W_IMG, H_IMG = args.width, args.height
+    from visual_odom_b200 import synth as _s
+    cal = _s.KITTI00 if args.calib == "kitti" else _s.ZED
+    units = [synth.stereo_unit(W_IMG, H_IMG, s, cal=cal) for s in range(args.units)]
     # each step = args.units frames on the CPU (bounded: steps+warmup passes over the same units)
     for _ in range(args.warmup):
         cpu_reference_frames(units, args.features, len(units))
@@ -161,7 +168,7 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world):
-    return {"workload": f"KITTI-00 shaped synthetic stereo {W_IMG}x{H_IMG}, {args.features} FAST features (thr 20, even-stride "
+    return {"workload": f"{args.calib}-calibrated synthetic stereo {W_IMG}x{H_IMG}, {args.features} FAST features (thr 20, even-stride "
                         f"selection), LK 21x21 maxLevel=3 (4 images) 30 it / 0.01, PnP RANSAC 500/0.5/0.999; "
                         f"{args.units} independent stereo pairs per step per GPU",
             "units_per_gpu": args.units, "global_units": args.units * world, "features": args.features,
@@ -170,7 +177,9 @@ def workload_config(args, world):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    global W_IMG, H_IMG
     args = parse()
+    W_IMG, H_IMG = args.width, args.height
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +205,8 @@ def main():
     table = vd.broadcast_unit_table(np.arange(world * B) if rank == 0 else np.zeros(world * B, np.int64), device="cuda")
     my_units = vd.unit_assignment(world * B, world)[rank]
     seeds = [int(table[u]) for u in my_units]
-    units = [synth.stereo_unit(W_IMG, H_IMG, s) for s in seeds]
+    cal = synth.KITTI00 if args.calib == "kitti" else synth.ZED
+    units = [synth.stereo_unit(W_IMG, H_IMG, s, cal=cal) for s in seeds]
 
     # pinned host copies of the images (what a capture / decode thread would hand over)
     pinned = []

@@ -63,3 +63,35 @@ def test_empty_and_tiny_inputs(ctx):
     from oracle import cref
     ro, rs, re = cref.lk_track(u["l0"], u["r0"], np.array([[100.5, 80.25]], np.float32))
     assert np.array_equal(o, ro) and np.array_equal(s, rs)
+
+
+def test_random_points_everywhere(ctx):
+    """Property-style sweep: points scattered far inside / on / outside the image (every early-out of
+    the level loop: prev window out of range, next window leaving the image mid-iteration, low
+    texture -> min-eigenvalue rejection) stay bit-identical to the oracle, status included."""
+    from oracle import cref
+    rng = np.random.default_rng(1234)
+    for (w, h, seed, scene) in [(300, 200, 1, "v0"), (96, 64, 2, "v0"), (1241, 376, 3, "v1")]:
+        u = synth.stereo_unit(w, h, seed, scene=scene)
+        a, b = u["l0"].copy(), u["l1"].copy()
+        a[h // 3: h // 3 + 40, w // 4: w // 4 + 60] = 128          # a flat patch: minEig < 1e-3
+        b[h // 3: h // 3 + 40, w // 4: w // 4 + 60] = 128
+        n = 1200
+        pts = np.stack([rng.uniform(-60, w + 60, n), rng.uniform(-60, h + 60, n)], 1).astype(np.float32)
+        pts[:50] = np.round(pts[:50])                               # integer positions (zero fractional weights)
+        ro, rs, re = cref.lk_track(a, b, pts)
+        go, gs, ge = ctx.lk_track(a, b, pts)
+        assert np.array_equal(gs, rs) and np.array_equal(go, ro)
+        assert np.array_equal(ge[rs == 1], re[rs == 1])
+        assert 0 < rs.sum() < n                                     # both outcomes are exercised
+
+
+def test_pyramid_truncation_small_image(ctx):
+    """Levels not larger than the 21x21 window end the pyramid (OpenCV rule): 100x44 has 2 images."""
+    from oracle import cref
+    u = synth.stereo_unit(100, 44, 9, scene="v0")
+    assert cref.Pyramid(u["l0"]).nlevels() == 2
+    pts = np.array([[20.5, 12.25], [50, 22], [80.75, 30.5], [5, 40], [99, 43]], np.float32)
+    ro, rs, re = cref.lk_track(u["l0"], u["r0"], pts)
+    go, gs, ge = ctx.lk_track(u["l0"], u["r0"], pts)
+    assert np.array_equal(gs, rs) and np.array_equal(go, ro)

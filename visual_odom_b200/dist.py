@@ -43,24 +43,22 @@ def gather_records(local_records, local_unit_ids, n_units, device="cpu"):
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     per = (n_units + world - 1) // world
-    buf = torch.zeros((per, RECORD_LEN + 1), dtype=torch.float64, device=device)
-    buf[:, 0] = -1
-    for i, (uid, rec) in enumerate(zip(local_unit_ids, local_records)):
-        buf[i, 0] = uid
-        buf[i, 1:] = torch.as_tensor(rec, dtype=torch.float64)
+    host = np.zeros((per, RECORD_LEN + 1), np.float64)
+    host[:, 0] = -1
+    n_local = len(local_unit_ids)
+    if n_local:
+        host[:n_local, 0] = np.asarray(local_unit_ids, np.float64)
+        host[:n_local, 1:] = np.asarray(local_records, np.float64).reshape(n_local, RECORD_LEN)
+    buf = torch.from_numpy(host).to(device)
     if world > 1:
-        outs = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(outs, buf)
+        out = torch.empty((world, per, RECORD_LEN + 1), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(out.view(world * per, RECORD_LEN + 1), buf)
+        rows = out.view(world * per, RECORD_LEN + 1).cpu().numpy()
     else:
-        outs = [buf]
+        rows = host
+    rows = rows[rows[:, 0] >= 0]
     table = np.zeros((n_units, RECORD_LEN), np.float64)
-    seen = np.zeros(n_units, bool)
-    for o in outs:
-        o = o.cpu().numpy()
-        for row in o:
-            uid = int(row[0])
-            if uid >= 0:
-                table[uid] = row[1:]
-                seen[uid] = True
-    assert seen.all(), "some units were not processed by any rank"
+    ids = rows[:, 0].astype(np.int64)
+    table[ids] = rows[:, 1:]
+    assert len(np.unique(ids)) == n_units, "some units were not processed by any rank"
     return table
