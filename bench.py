@@ -257,6 +257,7 @@ def main():
 
     # ---------------- LK kernel alone (roofline): one stream, so its CUDA-event time is not shared ----------------
     ctx.set_option("batch_streams", 1)
+    ctx.set_option("graphs", 0)          # plain launches: the LK kernel is bracketed by its own CUDA events
     for _ in range(args.warmup):
         ctx.batch_run()
     torch.cuda.synchronize()
@@ -271,6 +272,7 @@ def main():
     t_single_ms = sum(a.elapsed_time(b) for a, b in ev1)
     lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
     ctx.set_option("batch_streams", 2)
+    ctx.set_option("graphs", 1)
 
     # ---------------- end-to-end through the C-ABI with host buffers (`e2e`) ----------------
     for _ in range(max(1, args.warmup)):

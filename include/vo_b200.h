@@ -77,7 +77,8 @@ VO_API long long vo_kernel_launches(const vo_ctx* ctx);
  * measured with CUDA events on the launching stream; n = launches counted. */
 VO_API int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset);
 /* Run-time knobs (measurement / debugging): "batch_streams" = 1|2 (unit ranges the batched path runs
- * concurrently, default 2), "lk_staging" = 0 (TMA, default) | 1 (plain loads). */
+ * concurrently, default 2), "lk_staging" = 0 (TMA, default) | 1 (plain loads), "graphs" = 1 (default: the
+ * batched path replays its kernel sequence as CUDA graphs) | 0 (plain launches; needed for vo_lk_kernel_time). */
 VO_API int vo_set_option(vo_ctx* ctx, const char* key, double value);
 
 /* ---- A1: cv::FAST(image, kps, threshold, nonmax) + KeyPoint::convert ------------------------

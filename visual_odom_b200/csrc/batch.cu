@@ -115,7 +115,7 @@ static int ensure_side_streams(vo_ctx* ctx)
 }
 
 // the whole path for the resident units of `v`, asynchronous on v.s
-static int run_range(vo_ctx* ctx, const View& v)
+static int run_range_launch(vo_ctx* ctx, const View& v)
 {
     ctx->imgs_per_unit = 4;
     int rc;
@@ -134,6 +134,38 @@ static int run_range(vo_ctx* ctx, const View& v)
                                                   ctx->d_n5 + v.u0, v.n, ctx->batch_detect ? 1 : 0);
     ctx->launches += 1;
     VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+// Replays (or first captures) the kernel sequence of one unit range as a CUDA graph on v.s.  All kernel
+// arguments are device pointers / sizes fixed by (range, detect, staging), so the graph is reusable until
+// the device state is re-allocated.  The LK event timing is not part of graphs.
+static int run_range(vo_ctx* ctx, const View& v)
+{
+    if (!ctx->use_graphs) return run_range_launch(ctx, v);
+    for (auto& g : ctx->graphs)
+        if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma) {
+            VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));
+            ctx->launches += g.launches;
+            return VO_OK;
+        }
+    const bool timing = ctx->lk_timing;
+    const long long before = ctx->launches;
+    ctx->lk_timing = false;
+    cudaGraph_t graph = nullptr;
+    VO_CUDA_CHECK(cudaStreamBeginCapture(v.s, cudaStreamCaptureModeThreadLocal));
+    int rc = run_range_launch(ctx, v);
+    cudaError_t e = cudaStreamEndCapture(v.s, &graph);
+    ctx->lk_timing = timing;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    VO_CUDA_CHECK(e);
+    vo_ctx::RangeGraph g;
+    g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma;
+    g.launches = ctx->launches - before;
+    VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->graphs.push_back(g);
+    VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));
     return VO_OK;
 }
 

@@ -109,6 +109,7 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (!ctx || !key) return VO_E_INVALID;
     if (strcmp(key, "batch_streams") == 0) { ctx->batch_streams = value >= 2 ? 2 : 1; return VO_OK; }
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
+    if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
     vo_set_error(ctx, "unknown option %s", key);
     return VO_E_INVALID;
 }
@@ -142,8 +143,15 @@ int vo_ensure_pinned(vo_ctx* ctx, size_t bytes)
 }
 
 // ---------------------------------------------------------------------------------------------
+void vo_drop_graphs(vo_ctx* ctx)
+{
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
 void vo_free_state(vo_ctx* ctx)
 {
+    vo_drop_graphs(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     ctx->allocs.clear();
     ctx->w = ctx->h = ctx->units = 0;

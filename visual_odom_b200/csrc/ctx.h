@@ -81,6 +81,9 @@ struct vo_ctx {
     int batch_uploaded = 0;         // units currently resident
     bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
     int batch_streams = 2;          // unit ranges run concurrently by the batched path
+    bool use_graphs = true;         // replay the per-range kernel sequence as a CUDA graph (no LK event timing then)
+    struct RangeGraph { int u0, n; bool detect, tma; cudaGraphExec_t exec; long long launches; };
+    std::vector<RangeGraph> graphs; // invalidated when the device state is re-allocated
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
     cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
@@ -89,6 +92,7 @@ struct vo_ctx {
 void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
 int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
 void vo_free_state(vo_ctx* ctx);
+void vo_drop_graphs(vo_ctx* ctx);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 // a contiguous range of resident work units processed on one stream
 struct View { int u0, n; cudaStream_t s; };
