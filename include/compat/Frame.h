@@ -1,4 +1,5 @@
-// compat/Frame.h -- the reference's Frame holder (reference src/Frame.h:12-36, src/Frame.cpp).
+// compat/Frame.h -- drop-in for the reference's Frame holder (reference src/Frame.h:12-36,
+// src/Frame.cpp:4-28): same members, same method names; triangulation runs on the GPU.
 #ifndef FRAME_H
 #define FRAME_H
 #include "vo_cv.h"
@@ -6,15 +7,17 @@
 
 class Frame {
 public:
+    // projection matrices (3x4 CV_32F), world pose, stereo features of this frame
+    cv::Mat m_projMatL, m_projMatR, m_worldRotation, m_worldTranslation;
+    std::vector<cv::Point2f> m_pointsFeatureLeft, m_pointsFeatureRight;
+
     Frame();
     Frame(int frameId, const cv::Mat projMatL, const cv::Mat projMatR, cv::Mat worldRotation, cv::Mat worldTranslation);
-    void setFeatures(std::vector<cv::Point2f> pointsFeatureLeft, std::vector<cv::Point2f> pointsFeatureRight);
-    // cv::triangulatePoints(m_projMatL, m_projMatR, left, right, points4D): 4 x N CV_32F homogeneous points.
-    // The GPU path returns the de-homogenised point (x, y, z, 1); see INTEGRATION.md.
-    void triangulateFeaturePoints(cv::Mat& points4D);
 
-    cv::Mat m_projMatL, m_projMatR;
-    cv::Mat m_worldRotation, m_worldTranslation;
-    std::vector<cv::Point2f> m_pointsFeatureLeft, m_pointsFeatureRight;
+    void setFeatures(std::vector<cv::Point2f> left, std::vector<cv::Point2f> right);
+    // cv::triangulatePoints(m_projMatL, m_projMatR, left, right, points4D) in the reference returns a
+    // unit-norm homogeneous 4 x N CV_32F matrix of arbitrary sign; here the same points come back
+    // de-homogenised as (x, y, z, 1) -- see INTEGRATION.md.
+    void triangulateFeaturePoints(cv::Mat& points4D);
 };
 #endif

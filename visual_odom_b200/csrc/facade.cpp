@@ -178,7 +178,7 @@ void circularMatching(cv::Mat img_l_0, cv::Mat img_r_0, cv::Mat img_l_1, cv::Mat
 }
 
 // ------------------------------------------------------------------------------------------------ bucket.h
-Bucket::Bucket(int size) : id(0), max_size(size) {}
+Bucket::Bucket(int capacity) : max_size(capacity), id(0) {}
 Bucket::~Bucket() {}
 int Bucket::size() { return (int)features.points.size(); }
 
