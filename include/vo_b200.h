@@ -166,6 +166,22 @@ VO_API int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t
 VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,
                           vo_point3f* X, int32_t* inliers);
 
+/* ---- streaming sequence mode ------------------------------------------------
+ * The state of the reference's main loop (src/main.cpp:87-92,123-181: currentVOFeatures, the previous
+ * stereo pair, `translation`) lives on the device.  vo_seq_begin uploads the first pair; each vo_seq_push
+ * uploads only the NEW pair, builds only its two pyramids and runs matchingFeatures() (FAST refill,
+ * bucketing rows/10 x 1, circular matching, 1-px round-trip check) -> triangulation ->
+ * trackingFrame2Frame(mono_rotation=false), carrying features / ages / translation to the next frame
+ * exactly as the reference does (including the ages-vs-points length skew).
+ *   out      counts + pose of this frame pair
+ *   pts4     optional: 4 arrays of pts_cap points (L0, R0, L1, R1 after the circular check) */
+VO_API int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
+                        const uint8_t* right0, size_t pitch);
+VO_API int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,
+                       vo_point2f* pts4, int pts_cap);
+/* currentVOFeatures (points / ages may differ in length) and the carried translation */
+VO_API int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap, int* n_points, int* n_ages, double t_out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,54 @@
+"""Streaming sequence mode (vo_seq_*): 20+ synthetic frames with the main-loop state (features, ages,
+translation) resident on the GPU, compared frame by frame with the reference path (cv2 through the
+verbatim glue of oracle/ref_path.py): FAST refill, bucketing (aliasing, age limit, overwrite rule),
+ages/points length skew, circular matching, triangulation, PnP with the carried extrinsic guess."""
+import numpy as np
+import pytest
+
+from visual_odom_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+STEP_R = np.array([0.001, -0.004, 0.0005])
+STEP_T = np.array([0.01, -0.003, -0.2])
+
+
+def _frames(w, h, seed, n):
+    base = synth.stereo_unit(w, h, seed)
+    out = [(base["l0"], base["r0"])]
+    for k in range(1, n):
+        u = synth.stereo_unit(w, h, seed, rvec=STEP_R * k, tvec=STEP_T * k)
+        out.append((u["l1"], u["r1"]))
+    return base, out
+
+
+@pytest.mark.parametrize("w,h,nf", [(1241, 376, 22), (640, 480, 6)])
+def test_sequence_state_carry_matches_reference(ctx, w, h, nf):
+    pytest.importorskip("cv2")
+    from oracle import ref_path
+    base, frames = _frames(w, h, 31, nf)
+    ctx.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
+    fs = ref_path.FeatureSet()
+    translation = np.zeros(3)
+    for k in range(1, nf):
+        l0, r0 = frames[k - 1]; l1, r1 = frames[k]
+        got = ctx.seq_push(l1, r1)
+        pL0, pR0, pL1, pR1, info = ref_path.matching_features(l0, r0, l1, r1, fs, backend="cv2")
+        X = ref_path.triangulate(base["P_l"], base["P_r"], pL0, pR0, "cv2")
+        R, translation, inl, rvec = ref_path.tracking_frame2frame(base["P_l"], pL0, pL1, X, translation, "cv2")
+        assert got["n_features"] == len(info["bucketed"]), f"frame {k}: bucketed feature count"
+        assert got["n_tracked"] == len(info["kept_idx"])
+        assert got["n_valid"] == len(pL0)
+        for name, ref in (("l0", pL0), ("r0", pR0), ("l1", pL1), ("r1", pR1)):
+            assert np.array_equal(got[name], ref), f"frame {k}: {name}"
+        assert got["n_inliers"] == len(inl), f"frame {k}: inlier count"
+        assert np.linalg.norm(got["R"] - R) / np.linalg.norm(R) <= 1e-4
+        assert np.linalg.norm(got["tvec"] - translation) / np.linalg.norm(translation) <= 1e-4
+        pts, ages, t = ctx.seq_state()
+        assert np.array_equal(pts, fs.points) and np.array_equal(ages, fs.ages), f"frame {k}: carried FeatureSet"
+        assert len(ages) >= len(pts)                       # the reference's ages/points skew is reproduced
+        assert got["n_valid"] > 50 and got["n_inliers"] > 20
+    # NB on this dense texture ages never exceed 1: the reference's one-slot buckets keep the LAST admitted
+    # feature and fresh FAST corners are appended after the tracked ones, so they overwrite them
+    #  -- reproduced, as the equality with fs.ages above shows.
+    assert ages.max() >= 1

@@ -71,6 +71,9 @@ SIGNATURES = {
     "vo_batch_run": (C.c_int, [C.c_void_p]),
     "vo_batch_download": (C.c_int, [C.c_void_p, C.POINTER(VoUnitResult), C.c_int]),
     "vo_frame_batch": (C.c_int, [C.c_void_p, C.POINTER(VoUnit), C.c_int, C.c_size_t, C.POINTER(VoUnitResult)]),
+    "vo_seq_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "vo_seq_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
+    "vo_seq_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -300,3 +303,26 @@ class Context:
         self._check(self.lib.vo_batch_fetch(self.h, unit, _p(pts_in), _p(pts4), _p(kept), _p(X), _p(inl)))
         return dict(pts_in=pts_in[:nf], l0=pts4[0, :nv], r0=pts4[1, :nv], l1=pts4[2, :nv], r1=pts4[3, :nv],
                     kept_idx=kept[:nv], X=X[:nv], inliers=inl[:ni])
+
+    # ---- streaming sequence mode -------------------------------------------------------------------
+    def seq_begin(self, left0, right0, P_l, P_r):
+        l = self._img(left0); r = self._img(right0)
+        assert l.shape == r.shape and l.strides == r.strides
+        P_l = np.ascontiguousarray(P_l, np.float32).reshape(12); P_r = np.ascontiguousarray(P_r, np.float32).reshape(12)
+        self._check(self.lib.vo_seq_begin(self.h, l.shape[1], l.shape[0], _p(P_l), _p(P_r), _p(l), _p(r), l.strides[0]))
+
+    def seq_push(self, left1, right1, pts_cap=4096):
+        l = self._img(left1); r = self._img(right1)
+        res = VoUnitResult()
+        pts4 = np.zeros((4, pts_cap, 2), np.float32)
+        self._check(self.lib.vo_seq_push(self.h, _p(l), _p(r), l.strides[0], C.byref(res), _p(pts4), pts_cap))
+        d = self._result_dict(res)
+        n = min(d["n_valid"], pts_cap)
+        d.update(l0=pts4[0, :n].copy(), r0=pts4[1, :n].copy(), l1=pts4[2, :n].copy(), r1=pts4[3, :n].copy())
+        return d
+
+    def seq_state(self, cap=1 << 17):
+        pts = np.zeros((cap, 2), np.float32); ages = np.zeros(cap, np.int32); t = np.zeros(3)
+        npts = C.c_int(); nages = C.c_int()
+        self._check(self.lib.vo_seq_state(self.h, _p(pts), _p(ages), cap, C.byref(npts), C.byref(nages), _p(t)))
+        return pts[:npts.value].copy(), ages[:nages.value].copy(), t

@@ -285,6 +285,14 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_counts, (size_t)units * its));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_inliers, uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_results, (size_t)units));
+    // sequence mode state
+    ctx->feat_cap = ctx->corner_cap + cap;
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_feat_pts, (size_t)ctx->feat_cap));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_feat_ages, (size_t)ctx->feat_cap));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_feat_cnt, (size_t)2));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_bucket, (size_t)ctx->bucket_cap));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_seq_err, (size_t)1));
+    ctx->seq_active = false;
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_results, 0, (size_t)units * sizeof(vo_unit_result_dev), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, (size_t)units * 3 * sizeof(double), ctx->stream));
     ctx->w = w; ctx->h = h; ctx->units = units;
@@ -295,18 +303,33 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
 }
 
 // ---------------------------------------------------------------------------------------------
+// pyramids (u8 + Scharr derivative, all levels) of the raw planes [plane0, plane0 + nplanes)
+int vo_run_pyramid(vo_ctx* ctx, int plane0, int nplanes, cudaStream_t s)
+{
+    PyrGeom pg = ctx->pg;
+    pg.n_img = nplanes;
+    for (int l = 0; l < pg.nlevels; l++) {
+        pg.lv[l].img += (size_t)plane0 * pg.lv[l].plane;
+        pg.lv[l].der += (size_t)plane0 * pg.lv[l].plane;
+    }
+    ctx->launches += vo_launch_pyramid(pg, ctx->d_raw_tab + plane0, ctx->w, s);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
 int vo_run_lk(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err)
+{
+    int rc = vo_run_pyramid(ctx, v.u0 * ctx->imgs_per_unit, v.n * ctx->imgs_per_unit, v.s);
+    if (rc) return rc;
+    return vo_run_lk_ring(ctx, v, ncalls, img_prev, img_next, want_err);
+}
+
+// the ring kernel alone (pyramids of every plane it touches must be up to date)
+int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err)
 {
     const int ipu = ctx->imgs_per_unit;
     const size_t uo = (size_t)v.u0 * ctx->cap;
-    PyrGeom pg = ctx->pg;
-    pg.n_img = v.n * ipu;
-    for (int l = 0; l < pg.nlevels; l++) {
-        pg.lv[l].img += (size_t)v.u0 * ipu * pg.lv[l].plane;
-        pg.lv[l].der += (size_t)v.u0 * ipu * pg.lv[l].plane;
-    }
-    ctx->launches += vo_launch_pyramid(pg, ctx->d_raw_tab + (size_t)v.u0 * ipu, ctx->w, v.s);
-    VO_CUDA_CHECK(cudaGetLastError());
+    const PyrGeom& pg = ctx->pg;
 
     LkArgs a;
     memset(&a, 0, sizeof(a));

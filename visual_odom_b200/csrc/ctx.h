@@ -5,6 +5,7 @@
 #include "filter.h"
 #include "fast.h"
 #include "pnp.h"
+#include "seq.h"
 #include "../../include/vo_b200.h"
 #include <vector>
 #include <stdarg.h>
@@ -62,6 +63,16 @@ struct vo_ctx {
     int* d_counts = nullptr;            // [units][iters]
     int* d_inliers = nullptr;           // [units][cap]
     vo_unit_result_dev* d_results = nullptr;   // [units]
+    // sequence mode (seq.cu): the reference main loop's state, device resident
+    float2* d_feat_pts = nullptr;       // [feat_cap] currentVOFeatures.points
+    int* d_feat_ages = nullptr;         // [feat_cap] currentVOFeatures.ages (may be longer than points)
+    int* d_feat_cnt = nullptr;          // [2] sizes of the two vectors
+    int* d_bucket = nullptr;            // [bucket_cap] scratch of bucketingFeatures
+    int* d_seq_err = nullptr;           // sticky error bits of the glue kernels
+    int feat_cap = 0, bucket_cap = 4096;
+    bool seq_active = false;
+    int seq_slot = 0;                   // raw/pyramid planes (2*slot, 2*slot+1) hold the previous stereo pair
+    long long seq_frames = 0;
     std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
 
     // ---- pinned host staging ------------------------------------------------------------------
@@ -98,6 +109,8 @@ int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 struct View { int u0, n; cudaStream_t s; };
 // run pyramids + LK (ncalls chained) for the units of `v`; images must already be in d_raw/d_raw_tab
 int vo_run_lk(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err);
+int vo_run_pyramid(vo_ctx* ctx, int plane0, int nplanes, cudaStream_t s);
+int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err);
 int vo_run_filter(vo_ctx* ctx, const View& v, bool with_ages);
 // FAST on raw plane `plane_in_unit` of each unit -> d_corners / d_ndet ; stride selection -> d_pts_in / d_npts
 int vo_run_fast(vo_ctx* ctx, const View& v, int plane_in_unit, bool want_resp);

@@ -1,0 +1,120 @@
+// seq_api.cu -- C-ABI of the streaming sequence mode (include/vo_b200.h, vo_seq_*).
+#include "ctx.h"
+#include <string.h>
+
+static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t* right, size_t pitch)
+{
+    const int w = ctx->w, h = ctx->h;
+    const uint8_t* imgs[2] = {left, right};
+    for (int k = 0; k < 2; k++) {
+        uint8_t* dst = ctx->d_raw + (size_t)(2 * slot + k) * w * h;
+        if (pitch == (size_t)w) VO_CUDA_CHECK(cudaMemcpyAsync(dst, imgs[k], (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+        else VO_CUDA_CHECK(cudaMemcpy2DAsync(dst, w, imgs[k], pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return VO_OK;
+}
+
+extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
+                            const uint8_t* right0, size_t pitch)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (!P_l || !P_r || !left0 || !right0 || w <= 0 || h <= 0 || pitch < (size_t)w) { vo_set_error(ctx, "vo_seq_begin: bad argument"); return VO_E_INVALID; }
+    if (h / 10 <= 0) { vo_set_error(ctx, "vo_seq_begin: image too small for the rows/10 bucket size"); return VO_E_UNSUPPORTED; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int rc = vo_ensure_state(ctx, w, h, 1, 4);
+    if (rc) return rc;
+    memcpy(ctx->P_l, P_l, 12 * sizeof(float));
+    memcpy(ctx->P_r, P_r, 12 * sizeof(float));
+    ctx->have_P = true;
+    ctx->imgs_per_unit = 4;
+    ctx->seq_slot = 0;
+    ctx->seq_frames = 0;
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_feat_cnt, 0, 2 * sizeof(int), ctx->stream));
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_seq_err, 0, sizeof(int), ctx->stream));
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, 3 * sizeof(double), ctx->stream));      // translation = zeros (main.cpp:82)
+    if ((rc = upload_pair(ctx, 0, left0, right0, pitch))) return rc;
+    if ((rc = vo_run_pyramid(ctx, 0, 2, ctx->stream))) return rc;
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->seq_active = true;
+    return VO_OK;
+}
+
+extern "C" int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,
+                           vo_point2f* pts4, int pts_cap)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (!ctx->seq_active) { vo_set_error(ctx, "vo_seq_push: call vo_seq_begin first"); return VO_E_INVALID; }
+    if (!left1 || !right1 || !out || pitch < (size_t)ctx->w) { vo_set_error(ctx, "vo_seq_push: bad argument"); return VO_E_INVALID; }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    ctx->imgs_per_unit = 4;
+    const int s0 = ctx->seq_slot, s1 = 1 - s0;
+    const int L0 = 2 * s0, R0 = 2 * s0 + 1, L1 = 2 * s1, R1 = 2 * s1 + 1;
+    const View v{0, 1, ctx->stream};
+    int rc;
+    // new stereo pair: upload + its two pyramids (the previous pair's pyramids are already resident)
+    if ((rc = upload_pair(ctx, s1, left1, right1, pitch))) return rc;
+    if ((rc = vo_run_pyramid(ctx, 2 * s1, 2, ctx->stream))) return rc;
+    // matchingFeatures(): FAST refill on the t0 left image -> bucketing -> circular matching -> filters
+    if ((rc = vo_run_fast(ctx, v, L0, false))) return rc;
+    SeqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.corners = ctx->d_corners; a.n_det = ctx->d_ndet; a.corner_cap = ctx->corner_cap;
+    a.feat_pts = ctx->d_feat_pts; a.feat_ages = ctx->d_feat_ages; a.cnt = ctx->d_feat_cnt; a.feat_cap = ctx->feat_cap;
+    a.refill_below = 2000;                                   // visualOdometry.cpp:95
+    a.rows = ctx->h; a.cols = ctx->w; a.bucket_size = ctx->h / 10;      // visualOdometry.cpp:106 (features_per_bucket = 1)
+    a.bucket = ctx->d_bucket; a.bucket_cap = ctx->bucket_cap;
+    a.out_pts = ctx->d_pts_in; a.out_ages = ctx->d_ages_in; a.out_n = ctx->d_npts; a.out_cap = ctx->cap;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    a.valid_l1 = ctx->d_valid4 + 2 * cs; a.n5 = ctx->d_n5; a.ages_out = ctx->d_ages_out; a.n3 = ctx->d_n3;
+    a.res = ctx->d_results; a.tprev = ctx->d_tprev; a.err = ctx->d_seq_err;
+    ctx->launches += vo_launch_seq_append(a, ctx->stream);
+    ctx->launches += vo_launch_seq_bucket(a, ctx->stream);
+    const int ip[4] = {L0, R0, R1, L1}, in[4] = {R0, R1, L1, L0};
+    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, v, true))) return rc;
+    // triangulation + pose
+    if ((rc = vo_run_triangulate(ctx, v, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
+    if ((rc = vo_run_pnp(ctx, v, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
+    // state carry: features.points = pointsLeft_t1, ages keep their A3 length, translation = tvec
+    ctx->launches += vo_launch_seq_update(a, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+
+    vo_unit_result_dev r;
+    int counts[4] = {0, 0, 0, 0}, err = 0;
+    VO_CUDA_CHECK(cudaMemcpyAsync(&r, ctx->d_results, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[0], ctx->d_npts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[1], ctx->d_ndet, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[2], ctx->d_n3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[3], ctx->d_n5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(&err, ctx->d_seq_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    r.n_features = counts[0]; r.n_detected = counts[1]; r.n_tracked = counts[2]; r.n_valid = counts[3];
+    memcpy(out, &r, sizeof(r));
+    if (pts4 && counts[3] > 0) {
+        const int n = counts[3] < pts_cap ? counts[3] : pts_cap;
+        for (int k = 0; k < 4; k++)
+            VO_CUDA_CHECK(cudaMemcpyAsync(pts4 + (size_t)k * pts_cap, ctx->d_valid4 + k * cs, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->seq_slot = s1;                 // imageLeft_t0 = imageLeft_t1 (main.cpp:157-158)
+    ctx->seq_frames++;
+    if (err) { vo_set_error(ctx, "vo_seq_push: glue kernel error bits 0x%x (1/2: capacity, 4: bucket grid, 8: feature outside the image)", err); return VO_E_CAPACITY; }
+    return VO_OK;
+}
+
+extern "C" int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap, int* n_points, int* n_ages, double t_out[3])
+{
+    if (!ctx || !ctx->seq_active) return VO_E_INVALID;
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int cnt[2] = {0, 0};
+    VO_CUDA_CHECK(cudaMemcpyAsync(cnt, ctx->d_feat_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (t_out) VO_CUDA_CHECK(cudaMemcpyAsync(t_out, ctx->d_tprev, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (n_points) *n_points = cnt[0];
+    if (n_ages) *n_ages = cnt[1];
+    if (points && cnt[0] > 0) VO_CUDA_CHECK(cudaMemcpyAsync(points, ctx->d_feat_pts, (size_t)(cnt[0] < cap ? cnt[0] : cap) * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ages && cnt[1] > 0) VO_CUDA_CHECK(cudaMemcpyAsync(ages, ctx->d_feat_ages, (size_t)(cnt[1] < cap ? cnt[1] : cap) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+}
