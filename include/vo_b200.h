@@ -182,6 +182,21 @@ VO_API int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1,
 /* currentVOFeatures (points / ages may differ in length) and the carried translation */
 VO_API int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap, int* n_points, int* n_ages, double t_out[3]);
 
+/* ---- pose bookkeeping -- host-only, O(1) per frame ---------------------------
+ * R is row-major 3x3, t is 3x1, frame_pose / rigid_inv are row-major 4x4 (the reference's CV_64F Mats).
+ *   vo_pose_is_rotation  replaces isRotationMatrix            (src/utils.cpp:93-102):  |I - R^T R|_F < 1e-6
+ *   vo_pose_euler        replaces rotationMatrixToEulerAngles (src/utils.cpp:107-131): float x,y,z
+ *   vo_pose_integrate    replaces integrateOdometryStereo     (src/utils.cpp:57-91):   rigid_inv (optional) =
+ *                        [R|t;0 0 0 1]^-1; frame_pose *= rigid_inv iff 0.05 < |t| < 10.  Returns 1 when the
+ *                        pose was advanced, 0 when the frame was skipped, <0 on a singular transform.
+ *   vo_pose_step         the main loop's gate + integration    (src/main.cpp:196-208):  all |euler| < 0.1
+ *   vo_seq_pose          frame_pose accumulated by vo_seq_push since vo_seq_begin */
+VO_API int  vo_pose_is_rotation(const double R[9]);
+VO_API void vo_pose_euler(const double R[9], float euler_xyz[3]);
+VO_API int  vo_pose_integrate(double frame_pose[16], const double R[9], const double t[3], double rigid_inv[16]);
+VO_API int  vo_pose_step(double frame_pose[16], const double R[9], const double t[3]);
+VO_API int  vo_seq_pose(vo_ctx* ctx, double frame_pose[16]);
+
 #ifdef __cplusplus
 }
 #endif

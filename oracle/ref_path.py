@@ -229,3 +229,24 @@ def tracking_frame2frame(P_l, pts_l0, pts_l1, X, translation, backend="cv2"):
     from . import pnp_ref
     res = pnp_ref.solve_pnp_ransac(X, pts_l1, K, np.zeros(3), translation, confidence=PNP_CONFIDENCE)
     return pnp_ref.rodrigues(res["rvec"]), res["tvec"], res["inliers"], res["rvec"]
+
+
+def rotation_matrix_to_euler_angles(R):
+    """utils.cpp:107-131 (sy is a float there)."""
+    sy = np.float32(np.sqrt(R[0, 0] * R[0, 0] + R[1, 0] * R[1, 0]))
+    if not sy < 1e-6:
+        return np.array([np.arctan2(R[2, 1], R[2, 2]), np.arctan2(-R[2, 0], float(sy)), np.arctan2(R[1, 0], R[0, 0])], np.float32)
+    return np.array([np.arctan2(-R[1, 2], R[1, 1]), np.arctan2(-R[2, 0], float(sy)), 0.0], np.float32)
+
+
+def integrate_pose(frame_pose, R, t):
+    """main.cpp:196-208 + utils.cpp:57-91: Euler gate (all |angles| < 0.1), then frame_pose *= [R|t]^-1
+    when 0.05 < |t| < 10."""
+    e = rotation_matrix_to_euler_angles(R)
+    if not (abs(e[1]) < 0.1 and abs(e[0]) < 0.1 and abs(e[2]) < 0.1):
+        return frame_pose
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+    scale = np.sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2])
+    if 0.05 < scale < 10:
+        return frame_pose @ np.linalg.inv(T)
+    return frame_pose

@@ -3,8 +3,11 @@
 //   usage: facade_main <in.bin> <out.bin>
 //   in : int32 w, h, n_frames ; float P_l[12], P_r[12] ; then n_frames x (left, right) u8 images
 //   out: per processed frame pair: int32 n ; n x (pL0, pR0, pL1, pR1) float2 ; n x float3 X ;
-//        int32 n_inl ; n_inl x int32 ; double R[9] ; double t[3] ; int32 n_features_after (currentVOFeatures)
+//        int32 n_inl ; n_inl x int32 ; double R[9] ; double t[3] ; int32 n_features_after (currentVOFeatures) ;
+//        double frame_pose[16] after the Euler gate + integrateOdometryStereo (reference src/main.cpp:196-208)
 #include "visualOdometry.h"
+#include "utils.h"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -28,6 +31,7 @@ int main(int argc, char** argv)
     cv::Mat rotation = cv::Mat::eye(3, 3, CV_64FC1);
     cv::Mat translation = cv::Mat::zeros(3, 1, CV_64FC1);
     FeatureSet currentVOFeatures;
+    cv::Mat frame_pose = cv::Mat::eye(4, 4, CV_64FC1);
     cv::Mat imageLeft_t0 = L[0], imageRight_t0 = R[0];
     for (int frame_id = 1; frame_id < nf; frame_id++) {
         cv::Mat imageLeft_t1 = L[frame_id], imageRight_t1 = R[frame_id];
@@ -49,6 +53,11 @@ int main(int argc, char** argv)
         std::fwrite(rotation.data, 8, 9, fo); std::fwrite(translation.data, 8, 3, fo);
         const int32_t na = (int32_t)currentVOFeatures.points.size();
         std::fwrite(&na, 4, 1, fo);
+        cv::Vec3f e = rotationMatrixToEulerAngles(rotation);
+        cv::Mat rigid_body_transformation;
+        if (std::fabs(e[1]) < 0.1 && std::fabs(e[0]) < 0.1 && std::fabs(e[2]) < 0.1)
+            integrateOdometryStereo(frame_id, rigid_body_transformation, frame_pose, rotation, translation);
+        std::fwrite(frame_pose.data, 8, 16, fo);
     }
     std::fclose(fi); std::fclose(fo);
     return 0;

@@ -50,6 +50,7 @@ def test_facade_sequence_matches_reference(built, tmp_path):
 
     fs = ref_path.FeatureSet()
     translation = np.zeros(3)
+    frame_pose = np.eye(4)
     for k in range(1, nf):
         l0, r0 = frames[k - 1]; l1, r1 = frames[k]
         pL0, pR0, pL1, pR1, info = ref_path.matching_features(l0, r0, l1, r1, fs, backend="cv2")
@@ -66,4 +67,7 @@ def test_facade_sequence_matches_reference(built, tmp_path):
         assert np.linalg.norm(Rg - R) / np.linalg.norm(R) <= 1e-4
         assert np.linalg.norm(tg - translation) / np.linalg.norm(translation) <= 1e-4
         assert int(take(np.int32, 1)[0]) == fs.size()
+        frame_pose = ref_path.integrate_pose(frame_pose, R, translation)
+        pose_g = take(np.float64, 16).reshape(4, 4)
+        assert np.abs(pose_g - frame_pose).max() <= 1e-9 * max(1.0, np.abs(frame_pose).max())
         assert n > 100 and ni > 50

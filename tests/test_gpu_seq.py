@@ -30,6 +30,7 @@ def test_sequence_state_carry_matches_reference(ctx, w, h, nf):
     ctx.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
     fs = ref_path.FeatureSet()
     translation = np.zeros(3)
+    frame_pose = np.eye(4)
     for k in range(1, nf):
         l0, r0 = frames[k - 1]; l1, r1 = frames[k]
         got = ctx.seq_push(l1, r1)
@@ -44,6 +45,8 @@ def test_sequence_state_carry_matches_reference(ctx, w, h, nf):
         assert got["n_inliers"] == len(inl), f"frame {k}: inlier count"
         assert np.linalg.norm(got["R"] - R) / np.linalg.norm(R) <= 1e-4
         assert np.linalg.norm(got["tvec"] - translation) / np.linalg.norm(translation) <= 1e-4
+        frame_pose = ref_path.integrate_pose(frame_pose, R, translation)
+        assert np.abs(ctx.seq_pose() - frame_pose).max() <= 1e-6 * max(1.0, np.abs(frame_pose).max()), f"frame {k}: frame_pose"
         pts, ages, t = ctx.seq_state()
         assert np.array_equal(pts, fs.points) and np.array_equal(ages, fs.ages), f"frame {k}: carried FeatureSet"
         assert len(ages) >= len(pts)                       # the reference's ages/points skew is reproduced
@@ -52,3 +55,4 @@ def test_sequence_state_carry_matches_reference(ctx, w, h, nf):
     # feature and fresh FAST corners are appended after the tracked ones, so they overwrite them
     #  -- reproduced, as the equality with fs.ages above shows.
     assert ages.max() >= 1
+    assert np.linalg.norm(frame_pose[:3, 3]) > 0.1 * (nf - 1) * np.linalg.norm(STEP_T)   # the pose actually advanced

@@ -72,6 +72,7 @@ def build_native(verbose=False, force=False):
 
 FACADE_LIB = os.path.join(ROOT, "libvo_facade.so")
 FACADE_TEST = os.path.join(REPO, "tests", "cpp", "facade_main")
+UTILS_TEST = os.path.join(REPO, "tests", "cpp", "utils_main")
 
 
 def build_facade(force=False):
@@ -94,6 +95,14 @@ def build_facade(force=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("facade test driver build failed")
+    usrc = os.path.join(REPO, "tests", "cpp", "utils_main.cpp")
+    if force or _newer([usrc, FACADE_LIB], UTILS_TEST):
+        cmd = ["g++", "-O2", "-std=c++17", "-I", inc, usrc, "-o", UTILS_TEST, "-L", ROOT, "-lvo_facade", "-lvo_b200",
+               "-Wl,-rpath,$ORIGIN/../../visual_odom_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("utils test driver build failed")
     return FACADE_LIB
 
 

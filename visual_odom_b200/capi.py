@@ -74,6 +74,11 @@ SIGNATURES = {
     "vo_seq_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vo_seq_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
     "vo_seq_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "vo_pose_is_rotation": (C.c_int, [C.c_void_p]),
+    "vo_pose_euler": (None, [C.c_void_p, C.c_void_p]),
+    "vo_pose_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vo_pose_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vo_seq_pose": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -326,3 +331,41 @@ class Context:
         npts = C.c_int(); nages = C.c_int()
         self._check(self.lib.vo_seq_state(self.h, _p(pts), _p(ages), cap, C.byref(npts), C.byref(nages), _p(t)))
         return pts[:npts.value].copy(), ages[:nages.value].copy(), t
+
+    def seq_pose(self):
+        """frame_pose (4x4) integrated by seq_push since seq_begin (reference main.cpp:196-208)."""
+        pose = np.zeros((4, 4))
+        self._check(self.lib.vo_seq_pose(self.h, _p(pose)))
+        return pose
+
+
+# ---- host-only pose bookkeeping (SURVEY.md 8f row N2; no GPU needed) ------------------------------------------------
+def pose_euler(R):
+    R = np.ascontiguousarray(R, np.float64); e = np.zeros(3, np.float32)
+    load_library().vo_pose_euler(_p(R), _p(e))
+    return e
+
+
+def pose_is_rotation(R):
+    R = np.ascontiguousarray(R, np.float64)
+    return bool(load_library().vo_pose_is_rotation(_p(R)))
+
+
+def pose_integrate(frame_pose, R, t):
+    """integrateOdometryStereo: returns (new_pose, rigid_inv, advanced)."""
+    pose = np.array(frame_pose, np.float64).reshape(4, 4).copy(); inv = np.zeros((4, 4))
+    R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64).reshape(3)
+    rc = load_library().vo_pose_integrate(_p(pose), _p(R), _p(t), _p(inv))
+    if rc < 0:
+        raise RuntimeError("vo_pose_integrate: singular transformation")
+    return pose, inv, bool(rc)
+
+
+def pose_step(frame_pose, R, t):
+    """Euler gate + integration (main.cpp:196-208): returns (new_pose, advanced)."""
+    pose = np.array(frame_pose, np.float64).reshape(4, 4).copy()
+    R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64).reshape(3)
+    rc = load_library().vo_pose_step(_p(pose), _p(R), _p(t))
+    if rc < 0:
+        raise RuntimeError("vo_pose_step: singular transformation")
+    return pose, bool(rc)

@@ -73,6 +73,7 @@ struct vo_ctx {
     bool seq_active = false;
     int seq_slot = 0;                   // raw/pyramid planes (2*slot, 2*slot+1) hold the previous stereo pair
     long long seq_frames = 0;
+    double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
     std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
 
     // ---- pinned host staging ------------------------------------------------------------------

@@ -324,3 +324,52 @@ void Frame::triangulateFeaturePoints(cv::Mat& points4D)
         points4D.at<float>(3, i) = 1.f;
     }
 }
+
+// ------------------------------------------------------------------------------------------------ utils.h
+#include "../../include/compat/utils.h"
+
+static void mat_to_rt(const cv::Mat& rotation, const cv::Mat& translation, double R[9], double t[3])
+{
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) R[3 * r + c] = rotation.at<double>(r, c);
+        t[r] = translation.at<double>(r);
+    }
+}
+
+void integrateOdometryStereo(int /*frame_id*/, cv::Mat& rigid_body_transformation, cv::Mat& frame_pose,
+                             const cv::Mat& rotation, const cv::Mat& translation_stereo)
+{
+    double R[9], t[3], pose[16], inv[16];
+    mat_to_rt(rotation, translation_stereo, R, t);
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) pose[4 * r + c] = frame_pose.at<double>(r, c);
+    const int rc = vo_pose_integrate(pose, R, t, inv);
+    if (rc < 0) throw std::runtime_error("integrateOdometryStereo: singular transformation");
+    rigid_body_transformation = cv::Mat(4, 4, CV_64FC1);
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) rigid_body_transformation.at<double>(r, c) = inv[4 * r + c];
+    if (rc == 1) {
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) frame_pose.at<double>(r, c) = pose[4 * r + c];
+    } else {
+        std::printf("[WARNING] scale below 0.1, or incorrect translation\n");
+    }
+}
+
+bool isRotationMatrix(cv::Mat& R)
+{
+    double r9[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) r9[3 * r + c] = R.at<double>(r, c);
+    return vo_pose_is_rotation(r9) != 0;
+}
+
+cv::Vec3f rotationMatrixToEulerAngles(cv::Mat& R)
+{
+    double r9[9];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) r9[3 * r + c] = R.at<double>(r, c);
+    cv::Vec3f v;
+    vo_pose_euler(r9, v.val);
+    return v;
+}

@@ -29,6 +29,7 @@ extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], cons
     ctx->imgs_per_unit = 4;
     ctx->seq_slot = 0;
     ctx->seq_frames = 0;
+    for (int i = 0; i < 16; i++) ctx->seq_pose[i] = (i % 5 == 0) ? 1.0 : 0.0;
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_feat_cnt, 0, 2 * sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_seq_err, 0, sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, 3 * sizeof(double), ctx->stream));      // translation = zeros (main.cpp:82)
@@ -99,6 +100,7 @@ extern "C" int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* rig
     }
     ctx->seq_slot = s1;                 // imageLeft_t0 = imageLeft_t1 (main.cpp:157-158)
     ctx->seq_frames++;
+    if (r.pnp_status == VO_OK) vo_pose_step(ctx->seq_pose, r.R, r.tvec);   // main.cpp:196-208
     if (err) { vo_set_error(ctx, "vo_seq_push: glue kernel error bits 0x%x (1/2: capacity, 4: bucket grid, 8: feature outside the image)", err); return VO_E_CAPACITY; }
     return VO_OK;
 }
