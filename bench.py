@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--units", type=int, default=8, help="independent stereo pairs per step per GPU")
     ap.add_argument("--features", type=int, default=N_FEAT)
     ap.add_argument("--cpu-sample", type=int, default=12, help="frames timed for cpu_baseline")
+    ap.add_argument("--sequence", type=int, default=24,
+                    help="frames of the streaming-mode (vo_seq_push) side measurement at N=1; 0 = skip")
     ap.add_argument("--width", type=int, default=W_IMG)
     ap.add_argument("--height", type=int, default=H_IMG)
     ap.add_argument("--calib", default="kitti", choices=["kitti", "zed"], help="intrinsics of the synthetic rig")
@@ -130,6 +132,53 @@ def cpu_reference_frames(units, n_feat, frames, threads=None):
         one(units[i % len(units)])
     dt = time.perf_counter() - t0
     return frames / dt, dt, cv2.getNumThreads()
+
+
+def sequence_mode(ctx, torch, cal, n_frames):
+    """SURVEY.md 8f row N1, reported beside the headline: the reference's actual usage pattern -- one stereo pair
+    at a time through vo_seq_push (pinned host images in, pose out, main-loop state resident on the GPU) -- against
+    the same loop on the CPU (cv2 through oracle/ref_path.matching_features).  Latency-bound: ~300 bucketed
+    features per frame, one frame in flight."""
+    from oracle import ref_path
+    from visual_odom_b200 import synth
+    step_r = np.array([0.001, -0.004, 0.0005]); step_t = np.array([0.01, -0.003, -0.2])
+    base = synth.stereo_unit(W_IMG, H_IMG, 31, cal=cal)
+    frames = [(base["l0"], base["r0"])]
+    for k in range(1, n_frames + 1):
+        u = synth.stereo_unit(W_IMG, H_IMG, 31, rvec=step_r * k, tvec=step_t * k, cal=cal)
+        frames.append((u["l1"], u["r1"]))
+    pin = []
+    for l, r in frames:
+        a = torch.empty((2, H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
+        a.numpy()[0] = l; a.numpy()[1] = r
+        pin.append(a.numpy())
+    lat = []
+    for rep in range(2):                      # rep 0 warms up (graph capture), rep 1 is timed
+        ctx.seq_begin(pin[0][0], pin[0][1], base["P_l"], base["P_r"])
+        lat = []
+        t0 = time.perf_counter()
+        for k in range(1, n_frames + 1):
+            t1 = time.perf_counter()
+            got = ctx.seq_push(pin[k][0], pin[k][1], want_points=False)
+            lat.append(time.perf_counter() - t1)
+        dt = time.perf_counter() - t0
+    gpu_fps = n_frames / dt
+    pose = ctx.seq_pose()
+    # CPU: same loop, bounded sample
+    fs = ref_path.FeatureSet(); translation = np.zeros(3)
+    ncpu = min(n_frames, 12)
+    t0 = time.perf_counter()
+    for k in range(1, ncpu + 1):
+        l0, r0 = frames[k - 1]; l1, r1 = frames[k]
+        pL0, pR0, pL1, pR1, info = ref_path.matching_features(l0, r0, l1, r1, fs, backend="cv2")
+        X = ref_path.triangulate(base["P_l"], base["P_r"], pL0, pR0, "cv2")
+        R, translation, inl, rvec = ref_path.tracking_frame2frame(base["P_l"], pL0, pL1, X, translation, "cv2")
+    cpu_fps = ncpu / (time.perf_counter() - t0)
+    return {"value": gpu_fps, "unit": "frames/s", "frames": n_frames, "median_latency_ms": 1e3 * float(np.median(lat)),
+            "max_latency_ms": 1e3 * float(np.max(lat)), "cpu_reference": cpu_fps, "cpu_frames": ncpu,
+            "features_last_frame": int(got["n_features"]), "inliers_last_frame": int(got["n_inliers"]),
+            "pose_translation": [float(x) for x in pose[:3, 3]],
+            "note": "vo_seq_push wall clock per frame incl. H2D of the new pair and the pose read-back"}
 
 
 def run_reference(args, rank, world):
@@ -317,6 +366,12 @@ def main():
             except Exception:
                 traffic = None
         cpu_fps, cpu_dt, cores = cpu_reference_frames(units, args.features, args.cpu_sample)
+        seq = None
+        if world == 1 and args.sequence > 0:
+            try:
+                seq = sequence_mode(ctx, torch, cal, args.sequence)
+            except Exception as e:           # a side measurement must never cost the headline line
+                seq = {"error": str(e)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -336,6 +391,7 @@ def main():
                              "sample": f"{args.cpu_sample} frames of the same workload in {cpu_dt:.1f} s; cv2 (the OpenCV the "
                                        f"reference's calls resolve to) through oracle/ref_path.py glue; os.cpu_count()={os.cpu_count()}"},
             "clocks": clocks,
+            "sequence_mode": seq,
             "parity": {"n_valid": [r["n_valid"] for r in res], "n_inliers": [r["n_inliers"] for r in res]},
         }
         print(json.dumps(line))

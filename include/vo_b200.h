@@ -174,7 +174,9 @@ VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f*
  * trackingFrame2Frame(mono_rotation=false), carrying features / ages / translation to the next frame
  * exactly as the reference does (including the ages-vs-points length skew).
  *   out      counts + pose of this frame pair
- *   pts4     optional: 4 arrays of pts_cap points (L0, R0, L1, R1 after the circular check) */
+ *   pts4     optional: 4 arrays of pts_cap points (L0, R0, L1, R1 after the circular check); the first
+ *            out->n_valid entries of each are meaningful, the rest of the arrays is scratch
+ * The per-frame kernel sequence is replayed as a CUDA graph (one per ping-pong slot; option "graphs"). */
 VO_API int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
                         const uint8_t* right0, size_t pitch);
 VO_API int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,

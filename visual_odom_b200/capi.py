@@ -316,9 +316,12 @@ class Context:
         P_l = np.ascontiguousarray(P_l, np.float32).reshape(12); P_r = np.ascontiguousarray(P_r, np.float32).reshape(12)
         self._check(self.lib.vo_seq_begin(self.h, l.shape[1], l.shape[0], _p(P_l), _p(P_r), _p(l), _p(r), l.strides[0]))
 
-    def seq_push(self, left1, right1, pts_cap=4096):
+    def seq_push(self, left1, right1, pts_cap=4096, want_points=True):
         l = self._img(left1); r = self._img(right1)
         res = VoUnitResult()
+        if not want_points:
+            self._check(self.lib.vo_seq_push(self.h, _p(l), _p(r), l.strides[0], C.byref(res), None, 0))
+            return self._result_dict(res)
         pts4 = np.zeros((4, pts_cap, 2), np.float32)
         self._check(self.lib.vo_seq_push(self.h, _p(l), _p(r), l.strides[0], C.byref(res), _p(pts4), pts_cap))
         d = self._result_dict(res)

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(1024) k_seq_bucket(const float2* __restrict__ 
 __global__ void __launch_bounds__(256) k_seq_update(const float2* __restrict__ valid_l1, const int* __restrict__ n5,
                                                     const int* __restrict__ ages_out, const int* __restrict__ n3,
                                                     float2* feat_pts, int* feat_ages, int* cnt,
-                                                    const vo_unit_result_dev* __restrict__ res, double* tprev)
+                                                    vo_unit_result_dev* res, double* tprev,
+                                                    const int* __restrict__ n_feat, const int* __restrict__ n_det)
 {
     const int np = *n5, na = *n3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(np, na); i += gridDim.x * blockDim.x) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) k_seq_update(const float2* __restrict__ v
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         cnt[0] = np; cnt[1] = na;
         for (int k = 0; k < 3; k++) tprev[k] = res->tvec[k];
+        res->n_features = *n_feat; res->n_detected = *n_det; res->n_tracked = na; res->n_valid = np;
     }
 }
 
@@ -94,6 +96,6 @@ int vo_launch_seq_bucket(const SeqArgs& a, cudaStream_t s)
 }
 int vo_launch_seq_update(const SeqArgs& a, cudaStream_t s)
 {
-    k_seq_update<<<8, 256, 0, s>>>(a.valid_l1, a.n5, a.ages_out, a.n3, a.feat_pts, a.feat_ages, a.cnt, a.res, a.tprev);
+    k_seq_update<<<8, 256, 0, s>>>(a.valid_l1, a.n5, a.ages_out, a.n3, a.feat_pts, a.feat_ages, a.cnt, a.res, a.tprev, a.out_n, a.n_det);
     return 1;
 }

@@ -12,7 +12,7 @@ struct SeqArgs {
     float2* out_pts; int* out_ages; int* out_n; int out_cap;
     // update
     const float2* valid_l1; const int* n5; const int* ages_out; const int* n3;
-    const vo_unit_result_dev* res; double* tprev;
+    vo_unit_result_dev* res; double* tprev;
     int* err;
 };
 

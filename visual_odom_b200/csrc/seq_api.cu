@@ -14,6 +14,76 @@ static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t
     return VO_OK;
 }
 
+
+// the kernel sequence of one pushed frame; s0 = slot of the previous pair (planes 2*s0, 2*s0+1)
+static int seq_launch(vo_ctx* ctx, int s0)
+{
+    ctx->imgs_per_unit = 4;
+    const int s1 = 1 - s0;
+    const int L0 = 2 * s0, R0 = 2 * s0 + 1, L1 = 2 * s1, R1 = 2 * s1 + 1;
+    const View v{0, 1, ctx->stream};
+    int rc;
+    // the new pair's two pyramids (the previous pair's are already resident)
+    if ((rc = vo_run_pyramid(ctx, 2 * s1, 2, ctx->stream))) return rc;
+    // matchingFeatures(): FAST refill on the t0 left image -> bucketing -> circular matching -> filters
+    if ((rc = vo_run_fast(ctx, v, L0, false))) return rc;
+    SeqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.corners = ctx->d_corners; a.n_det = ctx->d_ndet; a.corner_cap = ctx->corner_cap;
+    a.feat_pts = ctx->d_feat_pts; a.feat_ages = ctx->d_feat_ages; a.cnt = ctx->d_feat_cnt; a.feat_cap = ctx->feat_cap;
+    a.refill_below = 2000;                                   // visualOdometry.cpp:95
+    a.rows = ctx->h; a.cols = ctx->w; a.bucket_size = ctx->h / 10;      // visualOdometry.cpp:106 (features_per_bucket = 1)
+    a.bucket = ctx->d_bucket; a.bucket_cap = ctx->bucket_cap;
+    a.out_pts = ctx->d_pts_in; a.out_ages = ctx->d_ages_in; a.out_n = ctx->d_npts; a.out_cap = ctx->cap;
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    a.valid_l1 = ctx->d_valid4 + 2 * cs; a.n5 = ctx->d_n5; a.ages_out = ctx->d_ages_out; a.n3 = ctx->d_n3;
+    a.res = ctx->d_results; a.tprev = ctx->d_tprev; a.err = ctx->d_seq_err;
+    ctx->launches += vo_launch_seq_append(a, ctx->stream);
+    ctx->launches += vo_launch_seq_bucket(a, ctx->stream);
+    const int ip[4] = {L0, R0, R1, L1}, in[4] = {R0, R1, L1, L0};
+    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
+    if ((rc = vo_run_filter(ctx, v, true))) return rc;
+    // triangulation + pose
+    if ((rc = vo_run_triangulate(ctx, v, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
+    if ((rc = vo_run_pnp(ctx, v, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
+    // state carry: features.points = pointsLeft_t1, ages keep their A3 length, translation = tvec; counts -> result record
+    ctx->launches += vo_launch_seq_update(a, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
+
+// replay (or first capture) the frame's kernel sequence as a CUDA graph; one graph per slot parity
+static int seq_run(vo_ctx* ctx, int s0)
+{
+    if (!ctx->use_graphs) return seq_launch(ctx, s0);
+    const int key = -1 - s0;
+    for (auto& g : ctx->graphs)
+        if (g.u0 == key && g.tma == ctx->lk_use_tma) {
+            VO_CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += g.launches;
+            return VO_OK;
+        }
+    const bool timing = ctx->lk_timing;
+    const long long before = ctx->launches;
+    ctx->lk_timing = false;
+    cudaGraph_t graph = nullptr;
+    VO_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = seq_launch(ctx, s0);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->lk_timing = timing;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    VO_CUDA_CHECK(e);
+    vo_ctx::RangeGraph g;
+    g.u0 = key; g.n = 1; g.detect = true; g.tma = ctx->lk_use_tma;
+    g.launches = ctx->launches - before;
+    VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->graphs.push_back(g);
+    VO_CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
+    return VO_OK;
+}
+
 extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
                             const uint8_t* right0, size_t pitch)
 {
@@ -47,57 +117,29 @@ extern "C" int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* rig
     if (!ctx->seq_active) { vo_set_error(ctx, "vo_seq_push: call vo_seq_begin first"); return VO_E_INVALID; }
     if (!left1 || !right1 || !out || pitch < (size_t)ctx->w) { vo_set_error(ctx, "vo_seq_push: bad argument"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    ctx->imgs_per_unit = 4;
     const int s0 = ctx->seq_slot, s1 = 1 - s0;
-    const int L0 = 2 * s0, R0 = 2 * s0 + 1, L1 = 2 * s1, R1 = 2 * s1 + 1;
-    const View v{0, 1, ctx->stream};
     int rc;
-    // new stereo pair: upload + its two pyramids (the previous pair's pyramids are already resident)
+    // new stereo pair -> device; then the frame's kernel sequence (a CUDA graph per slot parity)
     if ((rc = upload_pair(ctx, s1, left1, right1, pitch))) return rc;
-    if ((rc = vo_run_pyramid(ctx, 2 * s1, 2, ctx->stream))) return rc;
-    // matchingFeatures(): FAST refill on the t0 left image -> bucketing -> circular matching -> filters
-    if ((rc = vo_run_fast(ctx, v, L0, false))) return rc;
-    SeqArgs a;
-    memset(&a, 0, sizeof(a));
-    a.corners = ctx->d_corners; a.n_det = ctx->d_ndet; a.corner_cap = ctx->corner_cap;
-    a.feat_pts = ctx->d_feat_pts; a.feat_ages = ctx->d_feat_ages; a.cnt = ctx->d_feat_cnt; a.feat_cap = ctx->feat_cap;
-    a.refill_below = 2000;                                   // visualOdometry.cpp:95
-    a.rows = ctx->h; a.cols = ctx->w; a.bucket_size = ctx->h / 10;      // visualOdometry.cpp:106 (features_per_bucket = 1)
-    a.bucket = ctx->d_bucket; a.bucket_cap = ctx->bucket_cap;
-    a.out_pts = ctx->d_pts_in; a.out_ages = ctx->d_ages_in; a.out_n = ctx->d_npts; a.out_cap = ctx->cap;
-    const size_t cs = (size_t)ctx->units * ctx->cap;
-    a.valid_l1 = ctx->d_valid4 + 2 * cs; a.n5 = ctx->d_n5; a.ages_out = ctx->d_ages_out; a.n3 = ctx->d_n3;
-    a.res = ctx->d_results; a.tprev = ctx->d_tprev; a.err = ctx->d_seq_err;
-    ctx->launches += vo_launch_seq_append(a, ctx->stream);
-    ctx->launches += vo_launch_seq_bucket(a, ctx->stream);
-    const int ip[4] = {L0, R0, R1, L1}, in[4] = {R0, R1, L1, L0};
-    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
-    if ((rc = vo_run_filter(ctx, v, true))) return rc;
-    // triangulation + pose
-    if ((rc = vo_run_triangulate(ctx, v, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
-    float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
-    if ((rc = vo_run_pnp(ctx, v, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
-    // state carry: features.points = pointsLeft_t1, ages keep their A3 length, translation = tvec
-    ctx->launches += vo_launch_seq_update(a, ctx->stream);
-    VO_CUDA_CHECK(cudaGetLastError());
+    if ((rc = seq_run(ctx, s0))) return rc;
 
-    vo_unit_result_dev r;
-    int counts[4] = {0, 0, 0, 0}, err = 0;
-    VO_CUDA_CHECK(cudaMemcpyAsync(&r, ctx->d_results, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[0], ctx->d_npts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[1], ctx->d_ndet, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[2], ctx->d_n3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(&counts[3], ctx->d_n5, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaMemcpyAsync(&err, ctx->d_seq_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    r.n_features = counts[0]; r.n_detected = counts[1]; r.n_tracked = counts[2]; r.n_valid = counts[3];
-    memcpy(out, &r, sizeof(r));
-    if (pts4 && counts[3] > 0) {
-        const int n = counts[3] < pts_cap ? counts[3] : pts_cap;
+    // one pinned read-back: result record (counts packed by k_seq_update) + sticky error bits
+    if ((rc = vo_ensure_pinned(ctx, sizeof(vo_unit_result_dev) + 16))) return rc;
+    vo_unit_result_dev* hr = (vo_unit_result_dev*)ctx->h_pinned;
+    int* herr = (int*)((char*)ctx->h_pinned + sizeof(vo_unit_result_dev));
+    VO_CUDA_CHECK(cudaMemcpyAsync(hr, ctx->d_results, sizeof(*hr), cudaMemcpyDeviceToHost, ctx->stream));
+    VO_CUDA_CHECK(cudaMemcpyAsync(herr, ctx->d_seq_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t cs = (size_t)ctx->units * ctx->cap;
+    if (pts4 && pts_cap > 0) {
+        // n_valid is not known on the host yet: copy up to min(cap, pts_cap) slots of each list in the same batch
+        const int n = ctx->cap < pts_cap ? ctx->cap : pts_cap;
         for (int k = 0; k < 4; k++)
             VO_CUDA_CHECK(cudaMemcpyAsync(pts4 + (size_t)k * pts_cap, ctx->d_valid4 + k * cs, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
-        VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const vo_unit_result_dev r = *hr;
+    const int err = *herr;
+    memcpy(out, &r, sizeof(r));
     ctx->seq_slot = s1;                 // imageLeft_t0 = imageLeft_t1 (main.cpp:157-158)
     ctx->seq_frames++;
     if (r.pnp_status == VO_OK) vo_pose_step(ctx->seq_pose, r.R, r.tvec);   // main.cpp:196-208
