@@ -181,8 +181,40 @@ VO_API int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const fl
                         const uint8_t* right0, size_t pitch);
 VO_API int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,
                        vo_point2f* pts4, int pts_cap);
+/* same, for inputs with `channels` interleaved bytes per pixel: 1 = gray, 3 = BGR as cv::imread(IMREAD_COLOR) returns
+ * it -- the BGR bytes are uploaded as they are and converted on the device with cv::cvtColor(BGR2GRAY)'s fixed-point
+ * formula (reference src/utils.cpp:178-179,188-189) inside the frame's graph. */
+VO_API int vo_seq_begin_ex(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
+                           const uint8_t* right0, size_t pitch, int channels);
+VO_API int vo_seq_push_ex(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, int channels,
+                          vo_unit_result* out, vo_point2f* pts4, int pts_cap);
 /* currentVOFeatures (points / ages may differ in length) and the carried translation */
 VO_API int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap, int* n_points, int* n_ages, double t_out[3]);
+
+/* ---- image ingest ---------------------------------------------------------------
+ * What loadImageLeft / loadImageRight do (reference src/utils.cpp:172-190): read <dir>/image_0/%06d.png and
+ * <dir>/image_1/%06d.png with cv::imread(IMREAD_COLOR) and cvtColor(BGR2GRAY).  The decoder is host code
+ * (zlib inflate is a serial stream); the reader decodes AHEAD of the consumer on worker threads into a ring of
+ * pinned buffers, so vo_seq_push's upload is one async DMA per image.
+ *   vo_png_info / vo_png_decode   one PNG held in memory -> BGR (3 B/px) and/or gray (1 B/px); either may be NULL.
+ *                                 Non-interlaced PNGs of every colour type / bit depth; 16-bit -> 8-bit by the high
+ *                                 byte, alpha dropped (what IMREAD_COLOR does).  Errors: vo_png_last_error().
+ *   vo_reader_open                sequence_dir/image_{0,1}/%06d.png, frames first_frame .. first_frame+n_frames-1,
+ *                                 `threads` decoders, `depth` (>= 2) frames of pinned ring.  force_channels: 0 = gray
+ *                                 files are delivered as gray, colour files as BGR (device conversion); 1 / 3 force.
+ *   vo_reader_next                blocks until the next frame is decoded; the returned pointers stay valid until the
+ *                                 following vo_reader_next / vo_reader_close.
+ *   vo_bgr_to_gray                the device conversion on host buffers (stage-level entry point, for parity tests) */
+typedef struct vo_reader vo_reader;
+VO_API int vo_png_info(const uint8_t* file_bytes, size_t n, int* w, int* h, int* color_type, int* bit_depth);
+VO_API int vo_png_decode(const uint8_t* file_bytes, size_t n, uint8_t* bgr, size_t bgr_pitch, uint8_t* gray, size_t gray_pitch);
+VO_API const char* vo_png_last_error(void);
+VO_API vo_reader* vo_reader_open(const char* sequence_dir, int first_frame, int n_frames, int threads, int depth, int force_channels);
+VO_API int vo_reader_next(vo_reader* rd, const uint8_t** left, const uint8_t** right, int* w, int* h, size_t* pitch,
+                          int* channels, int* frame_id);
+VO_API const char* vo_reader_error(vo_reader* rd);
+VO_API void vo_reader_close(vo_reader* rd);
+VO_API int vo_bgr_to_gray(vo_ctx* ctx, const uint8_t* bgr, size_t pitch, int w, int h, uint8_t* gray, size_t gray_pitch);
 
 /* ---- pose bookkeeping -- host-only, O(1) per frame ---------------------------
  * R is row-major 3x3, t is 3x1, frame_pose / rigid_inv are row-major 4x4 (the reference's CV_64F Mats).

@@ -5,8 +5,34 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+// "load <dir/> <frame_id> <out>" mode: loadImageLeft + loadImageRight, writes int32 w,h then color(3wh) gray(wh) of
+// the left image and the same for the right one.
+#include <cstring>
+#include <string>
+static int load_mode(char** argv)
+{
+    cv::Mat c, g;
+    FILE* fo = std::fopen(argv[4], "wb");
+    if (!fo) return 3;
+    for (int cam = 0; cam < 2; cam++) {
+        try {
+            if (cam == 0) loadImageLeft(c, g, std::atoi(argv[3]), argv[2]);
+            else loadImageRight(c, g, std::atoi(argv[3]), argv[2]);
+        } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 6; }
+        const int32_t wh[2] = {c.cols, c.rows};
+        std::fwrite(wh, 4, 2, fo);
+        for (int r = 0; r < c.rows; r++) std::fwrite(c.data + r * c.step, 1, (size_t)3 * c.cols, fo);
+        for (int r = 0; r < g.rows; r++) std::fwrite(g.data + r * g.step, 1, (size_t)g.cols, fo);
+    }
+    std::fclose(fo);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc == 5 && !std::strcmp(argv[1], "load")) return load_mode(argv);
     if (argc < 3) return 2;
     FILE* fi = std::fopen(argv[1], "rb");
     FILE* fo = std::fopen(argv[2], "wb");

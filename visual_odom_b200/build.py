@@ -62,7 +62,7 @@ def build_native(verbose=False, force=False):
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if force or jobs or _newer(objs, LIB):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-o", LIB] + objs
+               "-o", LIB] + objs + ["-lz", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -74,6 +74,17 @@ SIGNATURES = {
     "vo_seq_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vo_seq_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
     "vo_seq_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    "vo_seq_begin_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "vo_seq_push_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
+    "vo_png_info": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vo_png_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "vo_png_last_error": (C.c_char_p, []),
+    "vo_reader_open": (C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vo_reader_next": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vo_reader_error": (C.c_char_p, [C.c_void_p]),
+    "vo_reader_close": (None, [C.c_void_p]),
+    "vo_bgr_to_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "vo_pose_is_rotation": (C.c_int, [C.c_void_p]),
     "vo_pose_euler": (None, [C.c_void_p, C.c_void_p]),
     "vo_pose_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -329,6 +340,41 @@ class Context:
         d.update(l0=pts4[0, :n].copy(), r0=pts4[1, :n].copy(), l1=pts4[2, :n].copy(), r1=pts4[3, :n].copy())
         return d
 
+    def seq_begin_bgr(self, left0, right0, P_l, P_r):
+        """Colour (H x W x 3, BGR) inputs: converted on the device like cv::cvtColor(BGR2GRAY)."""
+        l = np.ascontiguousarray(left0, np.uint8); r = np.ascontiguousarray(right0, np.uint8)
+        assert l.ndim == 3 and l.shape[2] == 3 and r.shape == l.shape
+        Pl = np.ascontiguousarray(P_l, np.float32); Pr = np.ascontiguousarray(P_r, np.float32)
+        self._check(self.lib.vo_seq_begin_ex(self.h, l.shape[1], l.shape[0], _p(Pl), _p(Pr), _p(l), _p(r), l.strides[0], 3))
+
+    def seq_push_bgr(self, left1, right1, pts_cap=4096):
+        l = np.ascontiguousarray(left1, np.uint8); r = np.ascontiguousarray(right1, np.uint8)
+        res = VoUnitResult()
+        pts4 = np.zeros((4, pts_cap, 2), np.float32)
+        self._check(self.lib.vo_seq_push_ex(self.h, _p(l), _p(r), l.strides[0], 3, C.byref(res), _p(pts4), pts_cap))
+        d = self._result_dict(res)
+        n = min(d["n_valid"], pts_cap)
+        d.update(l0=pts4[0, :n].copy(), r0=pts4[1, :n].copy(), l1=pts4[2, :n].copy(), r1=pts4[3, :n].copy())
+        return d
+
+    def seq_push_ptr(self, left_ptr, right_ptr, pitch, channels=1):
+        """Raw host pointers (e.g. the pinned buffers a SequenceReader hands out); returns counts + pose only."""
+        res = VoUnitResult()
+        self._check(self.lib.vo_seq_push_ex(self.h, left_ptr, right_ptr, pitch, channels, C.byref(res), None, 0))
+        return self._result_dict(res)
+
+    def seq_begin_ptr(self, w, h, left_ptr, right_ptr, pitch, P_l, P_r, channels=1):
+        Pl = np.ascontiguousarray(P_l, np.float32); Pr = np.ascontiguousarray(P_r, np.float32)
+        self._check(self.lib.vo_seq_begin_ex(self.h, w, h, _p(Pl), _p(Pr), left_ptr, right_ptr, pitch, channels))
+
+    def bgr_to_gray(self, bgr):
+        """Stage-level entry point of the device gray conversion (H x W x 3 uint8 -> H x W uint8)."""
+        a = np.ascontiguousarray(bgr, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 3
+        out = np.empty(a.shape[:2], np.uint8)
+        self._check(self.lib.vo_bgr_to_gray(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(out), out.strides[0]))
+        return out
+
     def seq_state(self, cap=1 << 17):
         pts = np.zeros((cap, 2), np.float32); ages = np.zeros(cap, np.int32); t = np.zeros(3)
         npts = C.c_int(); nages = C.c_int()
@@ -372,3 +418,65 @@ def pose_step(frame_pose, R, t):
     if rc < 0:
         raise RuntimeError("vo_pose_step: singular transformation")
     return pose, bool(rc)
+
+
+# ---- image ingest: host-side PNG decode + prefetching KITTI-layout reader ----------------------
+def png_info(data):
+    buf = np.frombuffer(data, np.uint8)
+    w = C.c_int(); h = C.c_int(); ct = C.c_int(); bd = C.c_int()
+    lib = load_library()
+    if lib.vo_png_info(_p(buf), buf.size, C.byref(w), C.byref(h), C.byref(ct), C.byref(bd)) != 0:
+        raise RuntimeError(lib.vo_png_last_error().decode())
+    return w.value, h.value, ct.value, bd.value
+
+
+def png_decode(data, want_bgr=True, want_gray=True):
+    """bytes of one PNG -> (bgr HxWx3 | None, gray HxW | None): imread(IMREAD_COLOR) and cvtColor(BGR2GRAY) of it."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, _, _ = png_info(data)
+    bgr = np.empty((h, w, 3), np.uint8) if want_bgr else None
+    gray = np.empty((h, w), np.uint8) if want_gray else None
+    lib = load_library()
+    rc = lib.vo_png_decode(_p(buf), buf.size, _p(bgr) if want_bgr else None, 3 * w, _p(gray) if want_gray else None, w)
+    if rc != 0:
+        raise RuntimeError(lib.vo_png_last_error().decode())
+    return bgr, gray
+
+
+class SequenceReader:
+    """<dir>/image_0/%06d.png + <dir>/image_1/%06d.png decoded ahead on worker threads into pinned buffers."""
+
+    def __init__(self, sequence_dir, first_frame, n_frames, threads=4, depth=4, force_channels=0):
+        self.lib = load_library()
+        self.h = self.lib.vo_reader_open(str(sequence_dir).encode(), first_frame, n_frames, threads, depth, force_channels)
+        if not self.h:
+            raise RuntimeError("vo_reader_open: " + self.lib.vo_png_last_error().decode())
+        self.n_frames = n_frames
+
+    def next_ptr(self):
+        """(left_ptr, right_ptr, w, h, pitch, channels, frame_id); pointers valid until the following call."""
+        l = C.c_void_p(); r = C.c_void_p(); w = C.c_int(); h = C.c_int(); p = C.c_size_t(); ch = C.c_int(); fid = C.c_int()
+        rc = self.lib.vo_reader_next(self.h, C.byref(l), C.byref(r), C.byref(w), C.byref(h), C.byref(p), C.byref(ch), C.byref(fid))
+        if rc != 0:
+            raise RuntimeError("vo_reader_next: " + self.lib.vo_reader_error(self.h).decode())
+        return l.value, r.value, w.value, h.value, p.value, ch.value, fid.value
+
+    def next(self):
+        """Copies of the frame's two images as numpy arrays (H x W or H x W x 3) + frame id."""
+        l, r, w, h, p, ch, fid = self.next_ptr()
+        shape = (h, w) if ch == 1 else (h, w, 3)
+        n = h * p
+        la = np.ctypeslib.as_array((C.c_uint8 * n).from_address(l)).reshape(shape).copy()
+        ra = np.ctypeslib.as_array((C.c_uint8 * n).from_address(r)).reshape(shape).copy()
+        return la, ra, fid
+
+    def close(self):
+        if self.h:
+            self.lib.vo_reader_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -83,6 +83,7 @@ extern "C" void vo_destroy(vo_ctx* ctx)
         if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_bgr) cudaFree(ctx->d_bgr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

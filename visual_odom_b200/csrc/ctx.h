@@ -74,6 +74,8 @@ struct vo_ctx {
     int seq_slot = 0;                   // raw/pyramid planes (2*slot, 2*slot+1) hold the previous stereo pair
     long long seq_frames = 0;
     double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
+    uint8_t* d_bgr = nullptr;           // staging of colour (BGR) inputs, converted by k_bgr_to_gray (ingest.cu)
+    size_t bgr_bytes = 0;
     std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
 
     // ---- pinned host staging ------------------------------------------------------------------
@@ -106,6 +108,9 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
 void vo_free_state(vo_ctx* ctx);
 void vo_drop_graphs(vo_ctx* ctx);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
+int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);
+int vo_launch_bgr_to_gray(const uint8_t* d_bgr, size_t pitch, size_t img_stride_in, uint8_t* d_gray, size_t img_stride_out,
+                          int w, int h, int n_img, cudaStream_t s);
 // a contiguous range of resident work units processed on one stream
 struct View { int u0, n; cudaStream_t s; };
 // run pyramids + LK (ncalls chained) for the units of `v`; images must already be in d_raw/d_raw_tab

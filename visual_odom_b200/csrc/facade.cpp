@@ -373,3 +373,27 @@ cv::Vec3f rotationMatrixToEulerAngles(cv::Mat& R)
     vo_pose_euler(r9, v.val);
     return v;
 }
+
+static void load_png_pair(cv::Mat& image_color, cv::Mat& image_gray, int cam, int frame_id, const std::string& filepath)
+{
+    char name[64];
+    std::snprintf(name, sizeof(name), "image_%d/%06d.png", cam, frame_id);
+    const std::string path = filepath + name;               // the reference concatenates, no separator added
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("loadImage: cannot open " + path);
+    std::vector<unsigned char> bytes;
+    unsigned char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+    std::fclose(f);
+    int w = 0, h = 0;
+    if (vo_png_info(bytes.data(), bytes.size(), &w, &h, nullptr, nullptr) != VO_OK)
+        throw std::runtime_error("loadImage: " + path + ": " + vo_png_last_error());
+    image_color = cv::Mat(h, w, CV_8UC3);
+    image_gray = cv::Mat(h, w, CV_8UC1);
+    if (vo_png_decode(bytes.data(), bytes.size(), image_color.data, image_color.step, image_gray.data, image_gray.step) != VO_OK)
+        throw std::runtime_error("loadImage: " + path + ": " + vo_png_last_error());
+}
+
+void loadImageLeft(cv::Mat& image_color, cv::Mat& image_gray, int frame_id, std::string filepath) { load_png_pair(image_color, image_gray, 0, frame_id, filepath); }
+void loadImageRight(cv::Mat& image_color, cv::Mat& image_gray, int frame_id, std::string filepath) { load_png_pair(image_color, image_gray, 1, frame_id, filepath); }

@@ -2,10 +2,18 @@
 #include "ctx.h"
 #include <string.h>
 
-static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t* right, size_t pitch)
+static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t* right, size_t pitch, int channels)
 {
     const int w = ctx->w, h = ctx->h;
     const uint8_t* imgs[2] = {left, right};
+    if (channels == 3) {                 // colour input: BGR bytes to the staging area, converted inside the frame's graph
+        const size_t img = (size_t)3 * w * h;
+        int rc = vo_ensure_bgr(ctx, 2 * img);
+        if (rc) return rc;
+        for (int k = 0; k < 2; k++)
+            VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_bgr + k * img, (size_t)3 * w, imgs[k], pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+        return VO_OK;
+    }
     for (int k = 0; k < 2; k++) {
         uint8_t* dst = ctx->d_raw + (size_t)(2 * slot + k) * w * h;
         if (pitch == (size_t)w) VO_CUDA_CHECK(cudaMemcpyAsync(dst, imgs[k], (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
@@ -14,15 +22,25 @@ static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t
     return VO_OK;
 }
 
+// BGR staging -> the two raw gray planes of `slot` (cv::cvtColor(BGR2GRAY) of utils.cpp:179,189)
+static int convert_pair(vo_ctx* ctx, int slot)
+{
+    const int w = ctx->w, h = ctx->h;
+    ctx->launches += vo_launch_bgr_to_gray(ctx->d_bgr, (size_t)3 * w, (size_t)3 * w * h, ctx->d_raw + (size_t)(2 * slot) * w * h,
+                                           (size_t)w * h, w, h, 2, ctx->stream);
+    VO_CUDA_CHECK(cudaGetLastError());
+    return VO_OK;
+}
 
 // the kernel sequence of one pushed frame; s0 = slot of the previous pair (planes 2*s0, 2*s0+1)
-static int seq_launch(vo_ctx* ctx, int s0)
+static int seq_launch(vo_ctx* ctx, int s0, bool bgr)
 {
     ctx->imgs_per_unit = 4;
     const int s1 = 1 - s0;
     const int L0 = 2 * s0, R0 = 2 * s0 + 1, L1 = 2 * s1, R1 = 2 * s1 + 1;
     const View v{0, 1, ctx->stream};
     int rc;
+    if (bgr && (rc = convert_pair(ctx, s1))) return rc;
     // the new pair's two pyramids (the previous pair's are already resident)
     if ((rc = vo_run_pyramid(ctx, 2 * s1, 2, ctx->stream))) return rc;
     // matchingFeatures(): FAST refill on the t0 left image -> bucketing -> circular matching -> filters
@@ -54,10 +72,10 @@ static int seq_launch(vo_ctx* ctx, int s0)
 }
 
 // replay (or first capture) the frame's kernel sequence as a CUDA graph; one graph per slot parity
-static int seq_run(vo_ctx* ctx, int s0)
+static int seq_run(vo_ctx* ctx, int s0, bool bgr)
 {
-    if (!ctx->use_graphs) return seq_launch(ctx, s0);
-    const int key = -1 - s0;
+    if (!ctx->use_graphs) return seq_launch(ctx, s0, bgr);
+    const int key = -1 - s0 - (bgr ? 2 : 0);
     for (auto& g : ctx->graphs)
         if (g.u0 == key && g.tma == ctx->lk_use_tma) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
@@ -69,7 +87,7 @@ static int seq_run(vo_ctx* ctx, int s0)
     ctx->lk_timing = false;
     cudaGraph_t graph = nullptr;
     VO_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = seq_launch(ctx, s0);
+    int rc = seq_launch(ctx, s0, bgr);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     ctx->lk_timing = timing;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -87,8 +105,15 @@ static int seq_run(vo_ctx* ctx, int s0)
 extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
                             const uint8_t* right0, size_t pitch)
 {
+    return vo_seq_begin_ex(ctx, w, h, P_l, P_r, left0, right0, pitch, 1);
+}
+
+extern "C" int vo_seq_begin_ex(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
+                               const uint8_t* right0, size_t pitch, int channels)
+{
     if (!ctx) return VO_E_INVALID;
-    if (!P_l || !P_r || !left0 || !right0 || w <= 0 || h <= 0 || pitch < (size_t)w) { vo_set_error(ctx, "vo_seq_begin: bad argument"); return VO_E_INVALID; }
+    if (channels != 1 && channels != 3) { vo_set_error(ctx, "vo_seq_begin: channels must be 1 (gray) or 3 (BGR)"); return VO_E_INVALID; }
+    if (!P_l || !P_r || !left0 || !right0 || w <= 0 || h <= 0 || pitch < (size_t)w * channels) { vo_set_error(ctx, "vo_seq_begin: bad argument"); return VO_E_INVALID; }
     if (h / 10 <= 0) { vo_set_error(ctx, "vo_seq_begin: image too small for the rows/10 bucket size"); return VO_E_UNSUPPORTED; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     int rc = vo_ensure_state(ctx, w, h, 1, 4);
@@ -103,7 +128,8 @@ extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], cons
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_feat_cnt, 0, 2 * sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_seq_err, 0, sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, 3 * sizeof(double), ctx->stream));      // translation = zeros (main.cpp:82)
-    if ((rc = upload_pair(ctx, 0, left0, right0, pitch))) return rc;
+    if ((rc = upload_pair(ctx, 0, left0, right0, pitch, channels))) return rc;
+    if (channels == 3 && (rc = convert_pair(ctx, 0))) return rc;
     if ((rc = vo_run_pyramid(ctx, 0, 2, ctx->stream))) return rc;
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->seq_active = true;
@@ -113,15 +139,22 @@ extern "C" int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], cons
 extern "C" int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,
                            vo_point2f* pts4, int pts_cap)
 {
+    return vo_seq_push_ex(ctx, left1, right1, pitch, 1, out, pts4, pts_cap);
+}
+
+extern "C" int vo_seq_push_ex(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, int channels,
+                              vo_unit_result* out, vo_point2f* pts4, int pts_cap)
+{
     if (!ctx) return VO_E_INVALID;
+    if (channels != 1 && channels != 3) { vo_set_error(ctx, "vo_seq_push: channels must be 1 (gray) or 3 (BGR)"); return VO_E_INVALID; }
     if (!ctx->seq_active) { vo_set_error(ctx, "vo_seq_push: call vo_seq_begin first"); return VO_E_INVALID; }
-    if (!left1 || !right1 || !out || pitch < (size_t)ctx->w) { vo_set_error(ctx, "vo_seq_push: bad argument"); return VO_E_INVALID; }
+    if (!left1 || !right1 || !out || pitch < (size_t)ctx->w * channels) { vo_set_error(ctx, "vo_seq_push: bad argument"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     const int s0 = ctx->seq_slot, s1 = 1 - s0;
     int rc;
     // new stereo pair -> device; then the frame's kernel sequence (a CUDA graph per slot parity)
-    if ((rc = upload_pair(ctx, s1, left1, right1, pitch))) return rc;
-    if ((rc = seq_run(ctx, s0))) return rc;
+    if ((rc = upload_pair(ctx, s1, left1, right1, pitch, channels))) return rc;
+    if ((rc = seq_run(ctx, s0, channels == 3))) return rc;
 
     // one pinned read-back: result record (counts packed by k_seq_update) + sticky error bits
     if ((rc = vo_ensure_pinned(ctx, sizeof(vo_unit_result_dev) + 16))) return rc;
