@@ -231,6 +231,22 @@ VO_API int  vo_pose_integrate(double frame_pose[16], const double R[9], const do
 VO_API int  vo_pose_step(double frame_pose[16], const double R[9], const double t[3]);
 VO_API int  vo_seq_pose(vo_ctx* ctx, double frame_pose[16]);
 
+/* ---- KITTI accuracy evaluation -- host-only, offline -----------------------------
+ * Poses are KITTI rows: 12 doubles = top 3 rows of the 4x4 camera-to-world matrix (what vo_seq_pose accumulates).
+ *   vo_poses_load / vo_poses_save   replace loadPoses (src/evaluate/evaluate_odometry.cpp:17-33; also read by
+ *                                   src/main.cpp for the ground-truth overlay) and the result writer
+ *   vo_eval_segments                replaces calcSequenceErrors (evaluate_odometry.cpp:71-116): start every `step`
+ *                                   (10) frames, segment lengths `lengths` (NULL = 100..800 m) along the ground-truth
+ *                                   path; per segment r_err [rad/m], t_err [fraction], speed [m/s at 10 Hz]
+ *   vo_eval_summary                 replaces saveStats (evaluate_odometry.cpp:376-395): mean t_err, r_err
+ * With out == NULL vo_eval_segments / vo_poses_load only count. */
+typedef struct vo_segment_error { int32_t first_frame; float r_err, t_err, len, speed; } vo_segment_error;
+VO_API int vo_poses_load(const char* path, double* poses12, int cap, int* n_out);
+VO_API int vo_poses_save(const char* path, const double* poses12, int n);
+VO_API int vo_eval_segments(const double* gt12, const double* est12, int n_poses, const float* lengths, int n_lengths,
+                            int step, vo_segment_error* out, int cap, int* n_out);
+VO_API int vo_eval_summary(const vo_segment_error* seg, int n, float* t_err_avg, float* r_err_avg);
+
 #ifdef __cplusplus
 }
 #endif

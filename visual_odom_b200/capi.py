@@ -85,6 +85,10 @@ SIGNATURES = {
     "vo_reader_error": (C.c_char_p, [C.c_void_p]),
     "vo_reader_close": (None, [C.c_void_p]),
     "vo_bgr_to_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "vo_poses_load": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "vo_poses_save": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int]),
+    "vo_eval_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "vo_eval_summary": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vo_pose_is_rotation": (C.c_int, [C.c_void_p]),
     "vo_pose_euler": (None, [C.c_void_p, C.c_void_p]),
     "vo_pose_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -480,3 +484,47 @@ class SequenceReader:
             self.close()
         except Exception:
             pass
+
+
+# ---- KITTI accuracy evaluation (host-only) -------------------------------------------------------
+SEGMENT_DTYPE = np.dtype([("first_frame", np.int32), ("r_err", np.float32), ("t_err", np.float32), ("len", np.float32),
+                          ("speed", np.float32)])
+
+
+def poses_load(path):
+    lib = load_library()
+    n = C.c_int()
+    if lib.vo_poses_load(str(path).encode(), None, 0, C.byref(n)) != 0:
+        raise RuntimeError(f"cannot read poses from {path}")
+    out = np.zeros((n.value, 12))
+    if n.value:
+        lib.vo_poses_load(str(path).encode(), _p(out), n.value, C.byref(n))
+    return out
+
+
+def poses_save(path, poses):
+    p = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(len(poses), -1)[:, :12])
+    if load_library().vo_poses_save(str(path).encode(), _p(p), len(p)) != 0:
+        raise RuntimeError(f"cannot write poses to {path}")
+
+
+def eval_segments(gt, est, lengths=None, step=10):
+    """KITTI segment errors of `est` against `gt` (n x 12 or n x 4 x 4 poses) -> (segments, t_err_avg, r_err_avg)."""
+    def rows(a):
+        a = np.asarray(a, np.float64)
+        return np.ascontiguousarray(a.reshape(len(a), -1)[:, :12])
+    g, e = rows(gt), rows(est)
+    assert g.shape == e.shape
+    lib = load_library()
+    L = np.ascontiguousarray(lengths, np.float32) if lengths is not None else None
+    n = C.c_int()
+    args = (_p(g), _p(e), len(g), _p(L) if L is not None else None, len(L) if L is not None else 0, step)
+    if lib.vo_eval_segments(*args, None, 0, C.byref(n)) != 0:
+        raise RuntimeError("vo_eval_segments failed (singular pose?)")
+    seg = np.zeros(n.value, SEGMENT_DTYPE)
+    if n.value == 0:
+        return seg, float("nan"), float("nan")
+    lib.vo_eval_segments(*args, _p(seg), n.value, C.byref(n))
+    t = C.c_float(); r = C.c_float()
+    lib.vo_eval_summary(_p(seg), n.value, C.byref(t), C.byref(r))
+    return seg, t.value, r.value
