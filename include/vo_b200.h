@@ -160,6 +160,15 @@ VO_API int vo_batch_run(vo_ctx* ctx);
 VO_API int vo_batch_download(vo_ctx* ctx, vo_unit_result* results, int n_units);
 /* upload + run + download in one call: the end-to-end entry point. */
 VO_API int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t pitch, vo_unit_result* results);
+/* Pipelined form of vo_frame_batch.  vo_batch_submit fills the resident unit slots [first_unit, first_unit + n_units)
+ * from units[0 .. n_units) (units == NULL: re-run what is resident there), runs the whole path on them and stages their
+ * result records, all asynchronously; vo_batch_wait blocks until that submission is done and copies the records out.
+ * Submissions on disjoint slot ranges overlap on the GPU (H2D and the latency-bound PnP tail of one under the LK ring of
+ * the other), e.g. configure 2 x B units and keep two submissions of B in flight.  The host images of a submission
+ * must stay valid (and, for a true async copy, be pinned) until it has been waited for; a slot range must be waited
+ * for before it is submitted again.  vo_batch_fetch of a waited slot is valid until that slot is resubmitted. */
+VO_API int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit, int n_units, size_t pitch);
+VO_API int vo_batch_wait(vo_ctx* ctx, int first_unit, int n_units, vo_unit_result* results);
 /* Fetch the per-unit arrays of the last run (any pointer may be NULL). Capacity = max_features.
  *   pts4: 4 x n_valid points (L0,R0,L1,R1 after A6);  kept_idx: n_valid original indices;
  *   X: n_valid 3-D points;  inliers: n_inliers indices into the n_valid list. */

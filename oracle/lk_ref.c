@@ -164,6 +164,81 @@ const int16_t *lk_pyr_level_deriv(const lk_pyr_t *p, int l) { return p->lv[l].de
 static int g_sum_mode = 0;
 void lk_set_sum_mode(int m) { g_sum_mode = m; }
 
+/* Optional bookkeeping for kernel design (not part of the checker): how often are all partial sums of the b chains
+ * exactly representable?  [0] iterations, [1] sum|addend| <= 2^24 on every chain (the kernel's current test),
+ * [2] strip bound: sum over the kernel's strips of max|running strip sum| <= 2^24 and every addend <= 2^24,
+ * [3] truth: every chain prefix and every addend <= 2^24 in magnitude. */
+static long long g_stats[8];
+static int g_stats_on = 0;
+void lk_stats_enable(int on) { g_stats_on = on; for (int i = 0; i < 8; i++) g_stats[i] = 0; }
+void lk_stats_get(long long *out) { for (int i = 0; i < 8; i++) out[i] = g_stats[i]; }
+
+static void lk_chain_stats(const int *diffs_all, const int16_t *dIbuf, int win)
+{
+    /* diffs_all: win x win residuals; dIbuf: win x win x 2 gradients */
+    const long long LIM = 1LL << 24;
+    int ok_old = 1, ok_strip = 1, ok_true = 1;
+    for (int comp = 0; comp < 2; comp++) {
+        /* SIMD chains q = 0..3: per row the pairs (q, q+4) then (q+8, q+12) */
+        for (int q = 0; q < 4; q++) {
+            long long sabs = 0, pre = 0, maxpre = 0, maxadd = 0;
+            for (int y = 0; y < win; y++)
+                for (int g = 0; g < 2; g++) {
+                    int x0 = q + 8 * g, x1 = x0 + 4;
+                    long long v0 = (long long)diffs_all[y * win + x0] * dIbuf[(y * win + x0) * 2 + comp];
+                    long long v1 = (long long)diffs_all[y * win + x1] * dIbuf[(y * win + x1) * 2 + comp];
+                    long long pair = v0 + v1;
+                    sabs += llabs(v0) + llabs(v1);
+                    pre += pair;
+                    if (llabs(pre) > maxpre) maxpre = llabs(pre);
+                    if (llabs(pair) > maxadd) maxadd = llabs(pair);
+                }
+            if (sabs > LIM) ok_old = 0;
+            if (maxpre > LIM || maxadd > LIM) ok_true = 0;
+            /* strip bound: strips (col, rows 0..10) and (col, rows 11..20) of the chain's 4 columns */
+            long long bound = 0, maxa = 0;
+            for (int c = q; c < 16; c += 4)
+                for (int half = 0; half < 2; half++) {
+                    long long run = 0, mx = 0;
+                    for (int y = half ? 11 : 0; y < (half ? win : 11); y++) {
+                        long long v = (long long)diffs_all[y * win + c] * dIbuf[(y * win + c) * 2 + comp];
+                        run += v;
+                        if (llabs(run) > mx) mx = llabs(run);
+                        if (llabs(v) > maxa) maxa = llabs(v);
+                    }
+                    bound += mx;
+                }
+            if (bound > LIM || 2 * maxa > LIM) ok_strip = 0;
+        }
+        /* tail chain: columns 16..20 row-major */
+        {
+            long long sabs = 0, pre = 0, maxpre = 0, maxadd = 0;
+            for (int y = 0; y < win; y++)
+                for (int x = 16; x < win; x++) {
+                    long long v = (long long)diffs_all[y * win + x] * dIbuf[(y * win + x) * 2 + comp];
+                    sabs += llabs(v); pre += v;
+                    if (llabs(pre) > maxpre) maxpre = llabs(pre);
+                    if (llabs(v) > maxadd) maxadd = llabs(v);
+                }
+            if (sabs > LIM) ok_old = 0;
+            if (maxpre > LIM || maxadd > LIM) ok_true = 0;
+            static const int seg_r0[6] = {0, 4, 8, 12, 15, 18}, seg_n[6] = {4, 4, 4, 3, 3, 3};
+            long long bound = 0;
+            for (int x = 16; x < win; x++)
+                for (int sg = 0; sg < 6; sg++) {
+                    long long run = 0, mx = 0;
+                    for (int y = seg_r0[sg]; y < seg_r0[sg] + seg_n[sg]; y++) {
+                        run += (long long)diffs_all[y * win + x] * dIbuf[(y * win + x) * 2 + comp];
+                        if (llabs(run) > mx) mx = llabs(run);
+                    }
+                    bound += mx;
+                }
+            if (bound > LIM || maxadd > LIM) ok_strip = 0;
+        }
+    }
+    g_stats[0]++; g_stats[1] += ok_old; g_stats[2] += ok_strip; g_stats[3] += ok_true;
+}
+
 static inline float reduce4(const float q[4])
 {
     switch (g_sum_mode) {
@@ -283,10 +358,11 @@ void lk_track(const lk_pyr_t *prev, const lk_pyr_t *next,
                 iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
                 float qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0};
                 float ib1 = 0, ib2 = 0;
+                int diffs_all[32 * 32];
                 for (int y = 0; y < win; y++) {
                     const uint8_t *Jp = Jbase + (y + iny) * J->istep + inx;
                     const int16_t *Ip = Ibuf + y * win, *dIp = dIbuf + y * win * 2;
-                    int diffs[64];
+                    int *diffs = diffs_all + y * win;
                     for (int x = 0; x < win; x++)
                         diffs[x] = DESCALE(Jp[x] * iw00 + Jp[x + 1] * iw01 +
                                            Jp[x + J->istep] * iw10 + Jp[x + J->istep + 1] * iw11, W_BITS - 5) - Ip[x];
@@ -310,6 +386,7 @@ void lk_track(const lk_pyr_t *prev, const lk_pyr_t *next,
                         ib2 += (float)(diffs[x] * dIp[2 * x + 1]);
                     }
                 }
+                if (g_stats_on && win == 21) lk_chain_stats(diffs_all, dIbuf, win);
                 if (g_sum_mode != 9) {
                     /* qf0 = interleave_pairs(qb0+qb1) low half = [s0, s2, 0, 0], qf1 = [s1, s3, 0, 0] */
                     float s[4];

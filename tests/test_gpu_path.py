@@ -82,3 +82,48 @@ def test_given_features_and_batch_independence(ctx):
         for k in ("kept_idx", "l0", "l1", "X", "inliers"):
             assert np.array_equal(g1[k], got3[i][k]), k
         assert np.array_equal(r1["rvec"], res3[i]["rvec"]) and np.array_equal(r1["tvec"], res3[i]["tvec"])
+
+
+def test_pipelined_submissions_equal_synchronous_batches(ctx):
+    """vo_batch_submit / vo_batch_wait: two slot ranges in flight give exactly the records and arrays of
+    vo_frame_batch on the same units, in any interleaving, including the re-run of resident slots."""
+    w, h, B = 640, 240, 3
+    sets = [[synth.stereo_unit(w, h, 10 * k + s) for s in range(B)] for k in range(4)]
+    P_l, P_r = sets[0][0]["P_l"], sets[0][0]["P_r"]
+    # synchronous references
+    ctx.batch_configure(w, h, B, P_l, P_r)
+    ref = []
+    for us in sets:
+        arr, keep, pitch = ctx.make_units([dict(u, n_select=400, t_prev=(0, 0, -0.8)) for u in us])
+        res = ctx.frame_batch(arr, pitch)
+        ref.append((res, [ctx.batch_fetch(i, res[i]) for i in range(B)]))
+    # pipelined: slots [0,B) and [B,2B), submit k+1 before waiting for k
+    ctx.batch_configure(w, h, 2 * B, P_l, P_r)
+    arrs = [ctx.make_units([dict(u, n_select=400, t_prev=(0, 0, -0.8)) for u in us]) for us in sets]
+    ctx.batch_submit(arrs[0][0], 0, arrs[0][2])
+    for k in range(len(sets)):
+        if k + 1 < len(sets):
+            ctx.batch_submit(arrs[k + 1][0], ((k + 1) % 2) * B, arrs[k + 1][2])
+        s0 = (k % 2) * B
+        res = ctx.batch_wait(s0, B)
+        for i in range(B):
+            r, rr = res[i], ref[k][0][i]
+            for key in ("n_features", "n_detected", "n_tracked", "n_valid", "n_inliers", "ransac_iters"):
+                assert r[key] == rr[key], (k, i, key)
+            assert np.array_equal(r["rvec"], rr["rvec"]) and np.array_equal(r["tvec"], rr["tvec"])
+            g = ctx.batch_fetch(s0 + i, r)
+            for key in ("kept_idx", "l0", "r0", "l1", "r1", "X", "inliers"):
+                assert np.array_equal(g[key], ref[k][1][i][key]), (k, i, key)
+    # re-run of what is resident (no upload): slot range [B, 2B) holds sets[3]
+    ctx.batch_submit(None, B, 0, n_units=B)
+    again = ctx.batch_wait(B, B)
+    assert all(np.array_equal(a["tvec"], r["tvec"]) and a["n_inliers"] == r["n_inliers"] for a, r in zip(again, ref[3][0]))
+    # misuse is reported, not undefined
+    ctx.batch_submit(arrs[0][0], 0, arrs[0][2])
+    with pytest.raises(RuntimeError, match="overlap"):
+        ctx.batch_submit(arrs[1][0], 1, arrs[1][2])
+    with pytest.raises(RuntimeError, match="no pending"):
+        ctx.batch_wait(B, B)
+    with pytest.raises(RuntimeError, match="outside"):
+        ctx.batch_submit(arrs[1][0], 2 * B - 1, arrs[1][2])
+    ctx.batch_wait(0, B)

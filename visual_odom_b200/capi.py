@@ -71,6 +71,8 @@ SIGNATURES = {
     "vo_batch_run": (C.c_int, [C.c_void_p]),
     "vo_batch_download": (C.c_int, [C.c_void_p, C.POINTER(VoUnitResult), C.c_int]),
     "vo_frame_batch": (C.c_int, [C.c_void_p, C.POINTER(VoUnit), C.c_int, C.c_size_t, C.POINTER(VoUnitResult)]),
+    "vo_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(VoUnit), C.c_int, C.c_int, C.c_size_t]),
+    "vo_batch_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(VoUnitResult)]),
     "vo_seq_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vo_seq_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
     "vo_seq_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
@@ -308,6 +310,19 @@ class Context:
     def frame_batch(self, arr, pitch):
         res = (VoUnitResult * len(arr))()
         self._check(self.lib.vo_frame_batch(self.h, arr, len(arr), pitch, res))
+        return [self._result_dict(r) for r in res]
+
+    def batch_submit(self, arr, first_unit, pitch, n_units=None):
+        """Asynchronous upload + run + result staging of resident slots [first_unit, first_unit + len(arr));
+        arr=None re-runs what is resident (n_units required)."""
+        if arr is None:
+            self._check(self.lib.vo_batch_submit(self.h, None, first_unit, n_units, pitch))
+        else:
+            self._check(self.lib.vo_batch_submit(self.h, arr, first_unit, len(arr), pitch))
+
+    def batch_wait(self, first_unit, n_units):
+        res = (VoUnitResult * n_units)()
+        self._check(self.lib.vo_batch_wait(self.h, first_unit, n_units, res))
         return [self._result_dict(r) for r in res]
 
     @staticmethod

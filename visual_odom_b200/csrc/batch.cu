@@ -35,14 +35,15 @@ extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const 
 }
 
 // H2D of units [u0, u0+n) on stream `st`; scalars go through the pinned staging block (disjoint per unit)
-static int upload_range(vo_ctx* ctx, const vo_unit* units, int u0, int n, size_t pitch, cudaStream_t st, bool detect)
+static int upload_range(vo_ctx* ctx, const vo_unit* units, int u0, int n, size_t pitch, cudaStream_t st, bool detect, int src0 = -1)
 {
+    if (src0 < 0) src0 = u0;           // units[src0 + i] fills resident slot u0 + i
     const int w = ctx->w, h = ctx->h, cap = ctx->cap;
     const int total = ctx->batch_units;
     double* h_tprev = (double*)ctx->h_pinned;
     int* h_cnt = (int*)(h_tprev + 3 * (size_t)total);
     for (int u = u0; u < u0 + n; u++) {
-        const vo_unit& U = units[u];
+        const vo_unit& U = units[u - u0 + src0];
         const uint8_t* imgs[4] = {U.l0, U.r0, U.l1, U.r1};
         for (int k = 0; k < 4; k++) {
             uint8_t* dst = ctx->d_raw + ((size_t)u * 4 + k) * w * h;
@@ -95,6 +96,7 @@ extern "C" int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, s
     int rc = validate_units(ctx, units, n_units, pitch, &detect, &max_pts);
     if (rc) return rc;
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = vo_drain_pending(ctx))) return rc;
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // staging block may still be in flight
     if ((rc = upload_range(ctx, units, 0, n_units, pitch, ctx->stream, detect))) return rc;
     ctx->batch_uploaded = n_units;
@@ -216,6 +218,7 @@ extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, si
     if (!results) return VO_E_INVALID;
     if (!ctx->have_P) { vo_set_error(ctx, "vo_frame_batch: projection matrices not set"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = vo_drain_pending(ctx))) return rc;
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->batch_uploaded = n_units; ctx->batch_detect = detect; ctx->batch_max_pts = max_pts;
     vo_unit_result_dev* h_res = pinned_results(ctx);
@@ -242,6 +245,80 @@ extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, si
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     memcpy(results, h_res, (size_t)n_units * sizeof(vo_unit_result));
     return VO_OK;
+}
+
+// ---- pipelined submissions -------------------------------------------------------------------------------------
+// A submission fills the resident unit slots [first_unit, first_unit + n_units), runs the whole path on them and
+// copies their result records to pinned staging, all asynchronously on one of the two side streams (alternating).
+// Submissions on disjoint slot ranges overlap on the GPU: the H2D copy, FAST / pyramids and above all the
+// latency-bound PnP tail (a few warps for ~0.4 ms) of one run under the issue-bound LK ring of the other, which a
+// synchronous vo_frame_batch per batch cannot do for its last unit range.
+extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit, int n_units, size_t pitch)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (first_unit < 0 || n_units <= 0 || first_unit + n_units > ctx->batch_units) {
+        vo_set_error(ctx, "vo_batch_submit: slots [%d, %d) outside the configured batch (%d)", first_unit, first_unit + n_units, ctx->batch_units);
+        return VO_E_INVALID;
+    }
+    if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_submit: projection matrices not set"); return VO_E_INVALID; }
+    for (auto& p : ctx->pending)
+        if (p.active && first_unit < p.u0 + p.n && p.u0 < first_unit + n_units) {
+            vo_set_error(ctx, "vo_batch_submit: slots [%d, %d) overlap a submission that has not been waited for", first_unit, first_unit + n_units);
+            return VO_E_INVALID;
+        }
+    bool detect = ctx->batch_detect; int max_pts = ctx->batch_max_pts;
+    int rc;
+    if (units) {
+        if ((rc = validate_units(ctx, units, n_units, pitch, &detect, &max_pts))) return rc;
+    } else {
+        if (ctx->batch_uploaded < first_unit + n_units) {
+            vo_set_error(ctx, "vo_batch_submit: units == NULL but slots [%d, %d) were never uploaded", first_unit, first_unit + n_units);
+            return VO_E_INVALID;
+        }
+        const size_t bytes = (size_t)ctx->batch_units * (3 * sizeof(double) + sizeof(int) + sizeof(vo_unit_result_dev)) + 256;
+        if ((rc = vo_ensure_pinned(ctx, bytes))) return rc;
+    }
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_side_streams(ctx))) return rc;
+    vo_ctx::Pending* slot = nullptr;
+    for (auto& p : ctx->pending) if (!p.active) { slot = &p; break; }
+    if (!slot) {
+        ctx->pending.emplace_back();
+        slot = &ctx->pending.back();
+        VO_CUDA_CHECK(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
+    }
+    const int c = (ctx->submit_count++) & 1;
+    cudaStream_t st = ctx->side_stream[c];
+    VO_CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+    ctx->batch_detect = detect;
+    if (max_pts > ctx->batch_max_pts || units) ctx->batch_max_pts = max_pts;
+    if (units) {
+        if ((rc = upload_range(ctx, units, first_unit, n_units, pitch, st, detect, 0))) return rc;
+        if (ctx->batch_uploaded < first_unit + n_units) ctx->batch_uploaded = first_unit + n_units;
+    }
+    if ((rc = run_range(ctx, View{first_unit, n_units, st}))) return rc;
+    vo_unit_result_dev* h_res = pinned_results(ctx);
+    VO_CUDA_CHECK(cudaMemcpyAsync(h_res + first_unit, ctx->d_results + first_unit, (size_t)n_units * sizeof(vo_unit_result_dev), cudaMemcpyDeviceToHost, st));
+    VO_CUDA_CHECK(cudaEventRecord(slot->done, st));
+    slot->u0 = first_unit; slot->n = n_units; slot->active = true;
+    return VO_OK;
+}
+
+extern "C" int vo_batch_wait(vo_ctx* ctx, int first_unit, int n_units, vo_unit_result* results)
+{
+    if (!ctx) return VO_E_INVALID;
+    for (auto& p : ctx->pending)
+        if (p.active && p.u0 == first_unit && p.n == n_units) {
+            VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+            VO_CUDA_CHECK(cudaEventSynchronize(p.done));
+            VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, p.done, 0));     // later work on the caller's stream sees the results
+            p.active = false;
+            if (results) memcpy(results, pinned_results(ctx) + first_unit, (size_t)n_units * sizeof(vo_unit_result));
+            return VO_OK;
+        }
+    vo_set_error(ctx, "vo_batch_wait: no pending submission for slots [%d, %d)", first_unit, first_unit + n_units);
+    return VO_E_INVALID;
 }
 
 extern "C" int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,

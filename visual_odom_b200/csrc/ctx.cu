@@ -74,9 +74,11 @@ extern "C" void vo_destroy(vo_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    vo_drain_pending(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     vo_free_state(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto& p : ctx->pending) if (p.done) cudaEventDestroy(p.done);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (int c = 0; c < 2; c++) {
         if (ctx->join_ev[c]) cudaEventDestroy(ctx->join_ev[c]);
@@ -140,6 +142,17 @@ int vo_ensure_pinned(vo_ctx* ctx, size_t bytes)
     if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; }
     VO_CUDA_CHECK(cudaMallocHost(&ctx->h_pinned, bytes));
     ctx->h_pinned_bytes = bytes;
+    return VO_OK;
+}
+
+// wait for every vo_batch_submit that was not waited for (before state is re-allocated, re-used synchronously or freed)
+int vo_drain_pending(vo_ctx* ctx)
+{
+    for (auto& p : ctx->pending)
+        if (p.active) {
+            VO_CUDA_CHECK(cudaEventSynchronize(p.done));
+            p.active = false;
+        }
     return VO_OK;
 }
 
@@ -218,6 +231,7 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
     if (w <= 0 || h <= 0 || units <= 0) { vo_set_error(ctx, "bad geometry %dx%d units=%d", w, h, units); return VO_E_INVALID; }
     if (ctx->w == w && ctx->h == h && ctx->units >= units) return VO_OK;
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    { int drc = vo_drain_pending(ctx); if (drc) return drc; }
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     vo_free_state(ctx);
     const int n_img = units * 4;

@@ -101,12 +101,16 @@ struct vo_ctx {
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
     cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+    struct Pending { int u0 = 0, n = 0; bool active = false; cudaEvent_t done = nullptr; };
+    std::vector<Pending> pending;   // vo_batch_submit / vo_batch_wait
+    unsigned submit_count = 0;
 };
 
 void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
 int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
 void vo_free_state(vo_ctx* ctx);
 void vo_drop_graphs(vo_ctx* ctx);
+int vo_drain_pending(vo_ctx* ctx);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);
 int vo_launch_bgr_to_gray(const uint8_t* d_bgr, size_t pitch, size_t img_stride_in, uint8_t* d_gray, size_t img_stride_out,
