@@ -138,54 +138,54 @@ def cpu_reference_frames(units, n_feat, frames, threads=None):
 _POOL_STATE = {}
 
 
-def _pool_prepare(task):
-    seed, w, h, calib, n_feat, threads = task
+def _pool_init(w, h, calib, n_feat, threads):
+    """Runs once in every worker process: its own work unit + OpenCV thread count + one warm-up frame."""
     import cv2
     from visual_odom_b200 import synth
     cv2.setNumThreads(threads)
     cal = synth.KITTI00 if calib == "kitti" else synth.ZED
-    _POOL_STATE["unit"] = synth.stereo_unit(w, h, seed, cal=cal)
+    _POOL_STATE["unit"] = synth.stereo_unit(w, h, os.getpid() % 64, cal=cal)
     _POOL_STATE["n_feat"] = n_feat
-    _cpu_one_frame(_POOL_STATE["unit"], n_feat)                # warm-up
-    return os.getpid()
+    _cpu_one_frame(_POOL_STATE["unit"], n_feat)
 
 
 def _pool_run(reps):
-    t0 = time.perf_counter()
     for _ in range(reps):
         _cpu_one_frame(_POOL_STATE["unit"], _POOL_STATE["n_feat"])
-    return time.perf_counter() - t0
+    return reps
 
 
-def cpu_reference_parallel(n_proc, w, h, calib, n_feat, reps, threads_per_proc):
+def cpu_reference_parallel(n_proc, w, h, calib, n_feat, frames, threads_per_proc):
     """Independent work units on `n_proc` host processes at once (each with `threads_per_proc` OpenCV threads): what a
-    CPU deployment of the batched workload would do with all the cores.  Returns (frames/s, wall seconds)."""
+    CPU deployment of the batched workload would do with all the cores.  Returns (frames/s, wall seconds, frames)."""
     import multiprocessing as mp
     ctxm = mp.get_context("spawn")                 # no fork: OpenCV's thread pool does not survive one
-    with ctxm.Pool(n_proc) as pool:
-        pool.map(_pool_prepare, [(s, w, h, calib, n_feat, threads_per_proc) for s in range(n_proc)], chunksize=1)
+    with ctxm.Pool(n_proc, initializer=_pool_init, initargs=(w, h, calib, n_feat, threads_per_proc)) as pool:
+        pool.map(_pool_run, [1] * (2 * n_proc), chunksize=1)          # every worker initialised and warm
+        chunk = 2
+        tasks = max(n_proc, int(round(frames / chunk)))
+        tasks = ((tasks + n_proc - 1) // n_proc) * n_proc               # whole waves
         t0 = time.perf_counter()
-        pool.map(_pool_run, [reps] * n_proc, chunksize=1)
+        done = sum(pool.map(_pool_run, [chunk] * tasks, chunksize=1))
         dt = time.perf_counter() - t0
-    return n_proc * reps / dt, dt
+    return done / dt, dt, done
 
 
 def cpu_reference_best(units, args, frames):
     """The better of (a) sequential frames with OpenCV's internal threads and (b) one process per core group."""
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     fps_a, dt_a, cv_threads = cpu_reference_frames(units, args.features, frames)
-    best = {"value": fps_a, "cores": cv_threads, "seconds": dt_a,
+    best = {"value": fps_a, "cores": cv_threads, "seconds": dt_a, "frames": frames,
             "how": f"sequential frames, {cv_threads} OpenCV threads (cv2 default)"}
     tried = [f"sequential x{cv_threads} threads: {fps_a:.1f} fps"]
     try:
         n_proc = max(1, min(cores, 64))
         per = max(1, cores // n_proc)
-        reps = max(2, int(round(frames / n_proc)))
-        fps_b, dt_b = cpu_reference_parallel(n_proc, W_IMG, H_IMG, args.calib, args.features, reps, per)
+        fps_b, dt_b, done = cpu_reference_parallel(n_proc, W_IMG, H_IMG, args.calib, args.features, max(frames, 4 * n_proc), per)
         tried.append(f"{n_proc} processes x{per} threads: {fps_b:.1f} fps")
         if fps_b > best["value"]:
-            best = {"value": fps_b, "cores": n_proc * per, "seconds": dt_b,
-                    "how": f"{n_proc} processes x {per} OpenCV thread(s), one work unit each, {reps} frames per process"}
+            best = {"value": fps_b, "cores": n_proc * per, "seconds": dt_b, "frames": done,
+                    "how": f"{n_proc} processes x {per} OpenCV thread(s), independent work units, {done} frames"}
     except Exception as e:                       # never lose the line to the pool
         tried.append(f"process pool failed: {str(e)[:80]}")
     best["tried"] = tried
@@ -265,7 +265,7 @@ def run_reference(args, rank, world):
         "dtype": "u8/i32 fixed point + f32 (LK), f64 (pose)", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{frames_total} frames of the workload in {best['seconds']:.1f} s; {best['how']}; cv2 "
+                         "sample": f"{best['frames']} frames of the workload in {best['seconds']:.1f} s; {best['how']}; cv2 "
                                    f"{__import__('cv2').__version__} (the OpenCV build the reference's calls resolve to) through the "
                                    f"oracle/ref_path.py glue restatement; affinity cores={best['affinity_cores']}; tried: {best['tried']}"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -480,7 +480,7 @@ def main():
                          "single_stream_ms_per_step": t_single_ms / args.steps,
                          "note": "algorithmic bytes per SURVEY.md 8(d); the kernel is ALU/latency bound, see DESIGN.md"},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.cpu_sample} frames of the same workload in {cpu_dt:.1f} s; {cpu_best['how']}; cv2 (the "
+                             "sample": f"{cpu_best['frames']} frames of the same workload in {cpu_dt:.1f} s; {cpu_best['how']}; cv2 (the "
                                        f"OpenCV the reference's calls resolve to) through oracle/ref_path.py glue; affinity cores="
                                        f"{cpu_best['affinity_cores']}; tried: {cpu_best['tried']}"},
             "clocks": clocks,

@@ -405,8 +405,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         if (e & 1) dpk[e >> 1] |= diff << 16; else dpk[e >> 1] = diff & 0xffff;
                         const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
                         const int vy = diff * (dxy[e] >> 16);
-                        if (part) { sxt += vx; syt += vy; axt += (unsigned)abs(vx); ayt += (unsigned)abs(vy); }
-                        else { sxs += vx; sys += vy; axs += (unsigned)abs(vx); ays += (unsigned)abs(vy); }
+                        // |v| + acc in one VABSDIFF (|v| <= 2^28, 15 of them per lane: no overflow)
+                        if (part) { sxt += vx; syt += vy; axt = __sad(vx, 0, axt); ayt = __sad(vy, 0, ayt); }
+                        else { sxs += vx; sys += vy; axs = __sad(vx, 0, axs); ays = __sad(vy, 0, ays); }
                         ptop = pbot;
                     }
                 }
