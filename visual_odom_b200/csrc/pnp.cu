@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(32 * 1) k_pnp_hypotheses(const PnpArgs a, int 
     __shared__ double sm_mtm[HYP_PER_CTA][144];
     __shared__ double sm_ut[HYP_PER_CTA][48];        // rows 11, 10, 9, 8 of U^T
     __shared__ int sm_rank_ok[HYP_PER_CTA];
-    Epnp5State st;
+    __shared__ Epnp5State sm_st[HYP_PER_CTA];
     if (work && r == 0) {
         const int* idx = a.subsets + ((size_t)unit * a.iterations + it) * 5;
         float Xs[15], xs[10];
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32 * 1) k_pnp_hypotheses(const PnpArgs a, int 
             Xs[3 * i] = P.x; Xs[3 * i + 1] = P.y; Xs[3 * i + 2] = P.z;
             xs[2 * i] = p.x; xs[2 * i + 1] = p.y;
         }
-        epnp5_front(Xs, xs, a.fu, a.fv, a.uc, a.vc, st, sm_mtm[g]);
+        epnp5_front(Xs, xs, a.fu, a.fv, a.uc, a.vc, sm_st[g], sm_mtm[g]);
     }
     __syncwarp();
     if (work) {          // uniform per 16-lane group
@@ -213,15 +213,39 @@ __global__ void __launch_bounds__(32 * 1) k_pnp_hypotheses(const PnpArgs a, int 
         if (r == 0) sm_rank_ok[g] = ok ? 1 : 0;
     }
     __syncwarp();
+    // EPnP tail: the three beta approximations are independent -> lanes 0..2 of the group run one each in lockstep
+    // (same instruction stream, run-time system width), lane 0 then picks like the reference (N = 1; 2 if err2 < err1;
+    // 3 if err3 < the best so far).  A rank-deficient M^T M (exactly-zero singular value) takes the sequential routine.
+    const bool fast_tail = work && sm_rank_ok[g];
+    double Rk[9], tk[3], errk = 0;
+    if (fast_tail && r < 3)
+        epnp5_back_one(sm_st[g], sm_ut[g], sm_ut[g] + 12, sm_ut[g] + 24, sm_ut[g] + 36, r + 1, Rk, tk, &errk);
+    __syncwarp();
+    if (fast_tail) {          // uniform per 16-lane group
+        const double e1 = __shfl_sync(gmask, errk, 16 * g + 1), e2 = __shfl_sync(gmask, errk, 16 * g + 2);
+        int pick = 0;
+        double best = errk;                       // lane 0's own value is approximation 1
+        if (r == 0) {
+            if (e1 < best) { best = e1; pick = 1; }
+            if (e2 < best) { best = e2; pick = 2; }
+        }
+        pick = __shfl_sync(gmask, pick, 16 * g);
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rk[k] = __shfl_sync(gmask, Rk[k], 16 * g + pick);
+#pragma unroll
+        for (int k = 0; k < 3; k++) tk[k] = __shfl_sync(gmask, tk[k], 16 * g + pick);
+    }
     if (work && r == 0) {
         double rvec[3], tvec[3], R[9];
-        if (sm_rank_ok[g]) {
-            epnp5_back(st, sm_ut[g], sm_ut[g] + 12, sm_ut[g] + 24, sm_ut[g] + 36, rvec, tvec, R);
+        if (fast_tail) {
+            rodrigues_inv(Rk, rvec);
+            for (int k = 0; k < 3; k++) tvec[k] = tk[k];
+            rodrigues_fwd(rvec, R);               // computeError -> projectPoints(rvec) converts back with Rodrigues
         } else {        // exactly-zero singular value: the sequential routine handles OpenCV's completion rule
             double ut[144], W12[12];
             for (int k = 0; k < 144; k++) ut[k] = sm_mtm[g][k];
             jacobi_svd_t<12, 12, false>(ut, W12, nullptr, 12);
-            epnp5_back(st, ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8, rvec, tvec, R);
+            epnp5_back(sm_st[g], ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8, rvec, tvec, R);
         }
         double* m = a.models + ((size_t)unit * a.iterations + it) * 12;
         for (int k = 0; k < 9; k++) m[k] = R[k];

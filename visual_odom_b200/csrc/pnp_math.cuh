@@ -16,9 +16,11 @@
 #if defined(__CUDACC__)
 #define VO_HD __host__ __device__ __forceinline__
 #define VO_HDN __host__ __device__
+#define VO_HDNI __host__ __device__ __noinline__      // one copy in the kernel: the hypothesis kernel is I-cache bound
 #else
 #define VO_HD inline
 #define VO_HDN
+#define VO_HDNI
 #endif
 
 namespace vomath {
@@ -153,6 +155,123 @@ VO_HDN void solve_svd(const double* A, const double* b, double* x)
     for (int i = 0; i < M; i++)
         for (int j = 0; j < N; j++) At[j * M + i] = A[i * N + j];
     jacobi_svd_t<M, N>(At, W, Vt, N);
+    double threshold = 0;
+    for (int i = 0; i < N; i++) threshold += W[i];
+    threshold *= kDblEps * 2;
+    for (int j = 0; j < N; j++) x[j] = 0;
+    for (int i = 0; i < N; i++) {
+        double wi = W[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        double s = 0;
+        for (int j = 0; j < M; j++) s += At[i * M + j] * b[j];
+        s *= wi;
+        for (int j = 0; j < N; j++) x[j] = x[j] + s * Vt[i * N + j];
+    }
+}
+
+// The same one-sided Jacobi with the column count N a RUN-TIME value (N <= NMAX): identical arithmetic and order as
+// jacobi_svd_t<M, N>, so lanes of one warp can solve systems of different widths in lockstep (EPnP's three beta
+// approximations are 6x4, 6x3 and 6x5 least-squares problems).  Rows of At / Vt are N-strided exactly like the template.
+template <int M, int NMAX>
+VO_HDN void jacobi_svd_rt(double* At, double* W, double* Vt, int N)
+{
+    const double eps = kDblEps * 10;
+    for (int i = 0; i < N; i++) {
+        double sd = 0;
+        for (int k = 0; k < M; k++) { double t = At[i * M + k]; sd += t * t; }
+        W[i] = sd;
+        for (int k = 0; k < N; k++) Vt[i * N + k] = 0;
+        Vt[i * N + i] = 1;
+    }
+    const int max_iter = M > 30 ? M : 30;
+    for (int iter = 0; iter < max_iter; iter++) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; i++)
+            for (int j = i + 1; j < N; j++) {
+                double* Ai = At + i * M; double* Aj = At + j * M;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < M; k++) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = cv_hypot(p, beta), c, s;
+                if (beta < 0) {
+                    double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < M; k++) {
+                    double t0 = c * Ai[k] + s * Aj[k];
+                    double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+                double* Vi = Vt + i * N; double* Vj = Vt + j * N;
+                for (int k = 0; k < N; k++) {
+                    double t0 = c * Vi[k] + s * Vj[k];
+                    double t1 = -s * Vi[k] + c * Vj[k];
+                    Vi[k] = t0; Vj[k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < N; i++) {
+        double sd = 0;
+        for (int k = 0; k < M; k++) { double t = At[i * M + k]; sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < N - 1; i++) {
+        int j = i;
+        for (int k = i + 1; k < N; k++)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < M; k++) { t = At[i * M + k]; At[i * M + k] = At[j * M + k]; At[j * M + k] = t; }
+            for (int k = 0; k < N; k++) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+        }
+    }
+    Rng rng(0x12345678);
+    for (int i = 0; i < N; i++) {
+        double sd = W[i];
+        for (int ii = 0; ii < 100 && sd <= kDblMin; ii++) {
+            const double val0 = 1. / M;
+            for (int k = 0; k < M; k++) At[i * M + k] = (rng.next() & 256) != 0 ? val0 : -val0;
+            for (int it = 0; it < 2; it++)
+                for (int j = 0; j < i; j++) {
+                    sd = 0;
+                    for (int k = 0; k < M; k++) sd += At[i * M + k] * At[j * M + k];
+                    double asum = 0;
+                    for (int k = 0; k < M; k++) {
+                        double t = At[i * M + k] - sd * At[j * M + k];
+                        At[i * M + k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < M; k++) At[i * M + k] *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < M; k++) { double t = At[i * M + k]; sd += t * t; }
+            sd = sqrt(sd);
+        }
+        const double s = sd > kDblMin ? 1 / sd : 0.;
+        for (int k = 0; k < M; k++) At[i * M + k] *= s;
+    }
+}
+
+// cv::solve(A (M x N row-major), b, x, DECOMP_SVD) with run-time N <= NMAX
+template <int M, int NMAX>
+VO_HDN void solve_svd_rt(const double* A, const double* b, double* x, int N)
+{
+    double At[NMAX * M], W[NMAX], Vt[NMAX * NMAX];
+    for (int i = 0; i < M; i++)
+        for (int j = 0; j < N; j++) At[j * M + i] = A[i * N + j];
+    jacobi_svd_rt<M, NMAX>(At, W, Vt, N);
     double threshold = 0;
     for (int i = 0; i < N; i++) threshold += W[i];
     threshold *= kDblEps * 2;
@@ -389,9 +508,13 @@ VO_HDN inline void epnp5_front(const float* Xw_f, const float* uv_f, double fu, 
 }
 
 // v0..v3: rows 11, 10, 9, 8 of U^T of the SVD of M^T M (12 doubles each)
-VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const double* v1, const double* v2, const double* v3,
-                              double* rvec, double* tvec, double* Rout)
+// One of EPnP's three beta initialisations (approx = 1: betas from [B11 B12 B13 B14], 2: [B11 B12 B22], 3: [B11 B12 B22 B13
+// B23]) -> Gauss-Newton -> R, t and the mean reprojection error of the 5 points.  The three are independent, so the
+// hypothesis kernel runs them on three lanes in lockstep (run-time system width) and picks like the reference does.
+VO_HDNI inline void epnp5_back_one(const Epnp5State& st, const double* v0, const double* v1, const double* v2, const double* v3,
+                                  int approx, double* R, double* t, double* err_out)
 {
+
     const int n = 5;
     const double (&X)[5][3] = st.X; const double (&us)[5][2] = st.us;
     const double (&cws)[4][3] = st.cws; const double (&al)[5][4] = st.al;
@@ -430,34 +553,28 @@ VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const doub
             if (b > 3) { a++; b = a + 1; }
         }
     }
-    double best_err = 0, best_R[9], best_t[3];
-    double x_last[4] = {0, 0, 0, 0};        // epnp::gauss_newton's x is zero-initialised once per call
-    for (int approx = 1; approx <= 3; approx++) {
+    double x_last[4] = {0, 0, 0, 0};
+    {
         double be[4];
-        if (approx == 1) {
-            double A[24], b4[4];
-            for (int i = 0; i < 6; i++) { A[i * 4] = L[i][0]; A[i * 4 + 1] = L[i][1]; A[i * 4 + 2] = L[i][3]; A[i * 4 + 3] = L[i][6]; }
-            solve_svd<6, 4>(A, rho, b4);
-            if (b4[0] < 0) { be[0] = sqrt(-b4[0]); be[1] = -b4[1] / be[0]; be[2] = -b4[2] / be[0]; be[3] = -b4[3] / be[0]; }
-            else { be[0] = sqrt(b4[0]); be[1] = b4[1] / be[0]; be[2] = b4[2] / be[0]; be[3] = b4[3] / be[0]; }
-        } else if (approx == 2) {
-            double A[18], b3[3];
-            for (int i = 0; i < 6; i++) { A[i * 3] = L[i][0]; A[i * 3 + 1] = L[i][1]; A[i * 3 + 2] = L[i][2]; }
-            solve_svd<6, 3>(A, rho, b3);
-            if (b3[0] < 0) { be[0] = sqrt(-b3[0]); be[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
-            else { be[0] = sqrt(b3[0]); be[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
-            if (b3[1] < 0) be[0] = -be[0];
-            be[2] = 0.0; be[3] = 0.0;
-        } else {
-            double A[30], b5[5];
-            for (int i = 0; i < 6; i++)
-                for (int c = 0; c < 5; c++) A[i * 5 + c] = L[i][c];
-            solve_svd<6, 5>(A, rho, b5);
-            if (b5[0] < 0) { be[0] = sqrt(-b5[0]); be[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
-            else { be[0] = sqrt(b5[0]); be[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
-            if (b5[1] < 0) be[0] = -be[0];
-            be[2] = b5[3] / be[0];
-            be[3] = 0.0;
+        {
+            // the beta estimate: least squares on the first ncol columns of L (in the order B11 B12 B13 B14 for approx 1)
+            const int ncol = approx == 1 ? 4 : (approx == 2 ? 3 : 5);
+            double A[30], bs[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < 6; i++) {
+                if (approx == 1) { A[i * 4] = L[i][0]; A[i * 4 + 1] = L[i][1]; A[i * 4 + 2] = L[i][3]; A[i * 4 + 3] = L[i][6]; }
+                else for (int c = 0; c < ncol; c++) A[i * ncol + c] = L[i][c];
+            }
+            solve_svd_rt<6, 5>(A, rho, bs, ncol);
+            if (approx == 1) {
+                if (bs[0] < 0) { be[0] = sqrt(-bs[0]); be[1] = -bs[1] / be[0]; be[2] = -bs[2] / be[0]; be[3] = -bs[3] / be[0]; }
+                else { be[0] = sqrt(bs[0]); be[1] = bs[1] / be[0]; be[2] = bs[2] / be[0]; be[3] = bs[3] / be[0]; }
+            } else {
+                if (bs[0] < 0) { be[0] = sqrt(-bs[0]); be[1] = (bs[2] < 0) ? sqrt(-bs[2]) : 0.0; }
+                else { be[0] = sqrt(bs[0]); be[1] = (bs[2] > 0) ? sqrt(bs[2]) : 0.0; }
+                if (bs[1] < 0) be[0] = -be[0];
+                be[2] = approx == 3 ? bs[3] / be[0] : 0.0;
+                be[3] = 0.0;
+            }
         }
         // gauss_newton: 5 iterations
         x_last[0] = x_last[1] = x_last[2] = x_last[3] = 0;
@@ -500,7 +617,7 @@ VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const doub
                 abt[3 * j + 1] += (pcs[i][j] - pc0[j]) * (X[i][1] - pw0[1]);
                 abt[3 * j + 2] += (pcs[i][j] - pc0[j]) * (X[i][2] - pw0[2]);
             }
-        double w3[3], U[9], Vt3[9], R[9], t[3];
+        double w3[3], U[9], Vt3[9];
         svd3(abt, w3, U, Vt3);
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++)      // dot(abt_u row i, abt_v row j), abt_v = V (not V^T)
@@ -519,11 +636,19 @@ VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const doub
             const double u = us[i][0], vv = us[i][1];
             sum2 += sqrt((u - ue) * (u - ue) + (vv - ve) * (vv - ve));
         }
-        const double err = sum2 / n;
-        bool take;
-        if (approx == 1) take = true;
-        else take = err < best_err;          // N = 2 if err2 < err1; N = 3 if err3 < err[N]
-        if (take) {
+        *err_out = sum2 / n;
+    }
+}
+
+VO_HDN inline void epnp5_back(const Epnp5State& st, const double* v0, const double* v1, const double* v2, const double* v3,
+                              double* rvec, double* tvec, double* Rout)
+{
+    double best_err = 0, best_R[9], best_t[3];
+    for (int approx = 1; approx <= 3; approx++) {
+        double R[9], t[3], err;
+        epnp5_back_one(st, v0, v1, v2, v3, approx, R, t, &err);
+        // N = 2 if err2 < err1; N = 3 if err3 < err[N]
+        if (approx == 1 || err < best_err) {
             best_err = err;
             for (int k = 0; k < 9; k++) best_R[k] = R[k];
             for (int k = 0; k < 3; k++) best_t[k] = t[k];
