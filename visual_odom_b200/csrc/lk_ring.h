@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 #define LK_WARPS_PER_CTA 1
-#define LK_MIN_CTAS_PER_SM 16
+#define LK_MIN_CTAS_PER_SM 17
 
 struct LkMaps {
     CUtensorMap img_i[VO_MAX_LEVELS];  // u8 planes, box 48 x 22 x 1 (I window, 16-byte aligned start)
