@@ -92,8 +92,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 #define DW 28                   // row pitch (uint32) of the derivative box
 #define I_ROWS 22
 #define J_ROWS 32
-#define CHS 132                 // floats per (quantity, chain) slot: >= 112 and == 4 (mod 32) so that the
-                                // 128-bit loads of the runner lanes fall into distinct bank groups
+#define CHS 116                 // floats per (quantity, chain) slot: >= 112 and CHS/4 odd, so that the 128-bit loads
+                                // of the runner lanes fall into distinct bank groups (132 worked as well; 116 lets
+                                // 17 CTAs fit in the SM's shared memory: 17 x (12416 + 1024 reserved) <= 228 KB)
 #define CHN 15                  // slots: 3 quantities x 5 chains
 struct __align__(128) WarpSmem {
     uint32_t dwin[DW * I_ROWS + 24];    // derivative window     (box 28 x 22 u32)  2464 -> 2560
@@ -102,7 +103,7 @@ struct __align__(128) WarpSmem {
     float chain[CHN * CHS];             // chain-ordered float addends (faithful summation); ALSO the landing zone
                                         // of the dense TMA boxes (I at +0, J at +1152 bytes) before re-pitching
     uint64_t bar;                       // mbarrier for TMA completion
-    uint64_t pad_[1];
+    uint64_t pad_[9];
 };
 #define RAW_I_OFF 0
 #define RAW_J_OFF 1152
