@@ -185,7 +185,7 @@ VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f*
  *   out      counts + pose of this frame pair
  *   pts4     optional: 4 arrays of pts_cap points (L0, R0, L1, R1 after the circular check); the first
  *            out->n_valid entries of each are meaningful, the rest of the arrays is scratch
- * The per-frame kernel sequence is replayed as a CUDA graph (one per ping-pong slot; option "graphs"). */
+ * The per-frame kernel sequence is replayed as two CUDA graphs (front half / pose solve; option "graphs"). */
 VO_API int vo_seq_begin(vo_ctx* ctx, int w, int h, const float P_l[12], const float P_r[12], const uint8_t* left0,
                         const uint8_t* right0, size_t pitch);
 VO_API int vo_seq_push(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, vo_unit_result* out,
@@ -197,7 +197,15 @@ VO_API int vo_seq_begin_ex(vo_ctx* ctx, int w, int h, const float P_l[12], const
                            const uint8_t* right0, size_t pitch, int channels);
 VO_API int vo_seq_push_ex(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, int channels,
                           vo_unit_result* out, vo_point2f* pts4, int pts_cap);
-/* currentVOFeatures (points / ages may differ in length) and the carried translation */
+/* Pipelined form: vo_seq_submit enqueues a frame and returns; vo_seq_wait blocks for the OLDEST frame in flight and
+ * returns its record (and integrates frame_pose).  At most two frames may be in flight: only the pose solve of frame
+ * k+1 depends on the pose solve of frame k (the extrinsic guess), so the upload, pyramids, FAST, bucketing, LK ring,
+ * filters and triangulation of frame k+1 run under the latency-bound PnP of frame k -- one frame of result lag buys
+ * ~1.7x the frame rate.  Results are identical to vo_seq_push (= submit + wait).  The host images of a submitted frame
+ * must stay valid until the call returns for pageable memory, until its vo_seq_wait for pinned memory. */
+VO_API int vo_seq_submit(vo_ctx* ctx, const uint8_t* left1, const uint8_t* right1, size_t pitch, int channels);
+VO_API int vo_seq_wait(vo_ctx* ctx, vo_unit_result* out, vo_point2f* pts4, int pts_cap);
+/* currentVOFeatures (points / ages may differ in length) and the carried translation (waits for frames in flight) */
 VO_API int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap, int* n_points, int* n_ages, double t_out[3]);
 
 /* ---- image ingest ---------------------------------------------------------------

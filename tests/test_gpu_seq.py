@@ -65,3 +65,42 @@ def test_sequence_state_carry_matches_reference(ctx, w, h, nf):
         from visual_odom_b200 import capi
         seg, t_err, r_err = capi.eval_segments(traj_ref, traj_gpu, lengths=[1.0, 2.0, 3.0], step=2)
         assert len(seg) >= 10 and t_err < 1e-6 and r_err < 1e-5
+
+
+def test_pipelined_submit_wait_equals_push(ctx):
+    """vo_seq_submit / vo_seq_wait with two frames in flight: identical records, point lists, pose and carried state
+    to the synchronous vo_seq_push, for gray and for colour input."""
+    w, h, nf = 1241, 376, 9
+    base, frames = _frames(w, h, 7, nf)
+    ctx.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
+    ref = [ctx.seq_push(l, r) for l, r in frames[1:]]
+    pose_ref = ctx.seq_pose()
+    state_ref = ctx.seq_state()
+
+    def check(got, k):
+        for key in ("n_features", "n_detected", "n_tracked", "n_valid", "n_inliers", "ransac_iters"):
+            assert got[key] == ref[k][key], (k, key)
+        for key in ("l0", "r0", "l1", "r1", "R", "tvec", "rvec"):
+            assert np.array_equal(got[key], ref[k][key]), (k, key)
+
+    ctx.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
+    ctx.seq_submit(frames[1][0], frames[1][1])
+    for k in range(1, nf):
+        if k + 1 < nf:
+            ctx.seq_submit(frames[k + 1][0], frames[k + 1][1])
+            if k == 1:
+                with pytest.raises(RuntimeError, match="in flight"):
+                    ctx.seq_submit(frames[k + 1][0], frames[k + 1][1])        # a third frame is refused
+        check(ctx.seq_wait(), k - 1)
+    with pytest.raises(RuntimeError, match="no frame in flight"):
+        ctx.seq_wait()
+    assert np.array_equal(ctx.seq_pose(), pose_ref)
+    st = ctx.seq_state()
+    assert all(np.array_equal(a, b) for a, b in zip(st, state_ref))
+    # mixing: a synchronous push while a frame is in flight is refused, then works after the wait
+    ctx.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
+    ctx.seq_submit(frames[1][0], frames[1][1])
+    with pytest.raises(RuntimeError, match="in flight"):
+        ctx.seq_push(frames[2][0], frames[2][1])
+    check(ctx.seq_wait(), 0)
+    check(ctx.seq_push(frames[2][0], frames[2][1]), 1)

@@ -75,6 +75,8 @@ SIGNATURES = {
     "vo_batch_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(VoUnitResult)]),
     "vo_seq_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vo_seq_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
+    "vo_seq_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "vo_seq_wait": (C.c_int, [C.c_void_p, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
     "vo_seq_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
     "vo_seq_begin_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "vo_seq_push_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(VoUnitResult), C.c_void_p, C.c_int]),
@@ -393,6 +395,28 @@ class Context:
         out = np.empty(a.shape[:2], np.uint8)
         self._check(self.lib.vo_bgr_to_gray(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(out), out.strides[0]))
         return out
+
+    def seq_submit(self, left1, right1):
+        """Asynchronous push (gray H x W or BGR H x W x 3); at most two frames in flight. Keep the arrays alive."""
+        l = np.asarray(left1); r = np.asarray(right1)
+        ch = 3 if l.ndim == 3 else 1
+        assert l.dtype == np.uint8 and l.shape == r.shape and l.strides[-1] == 1 and (ch == 1 or l.strides[1] == 3)
+        self._check(self.lib.vo_seq_submit(self.h, _p(l), _p(r), l.strides[0], ch))
+
+    def seq_submit_ptr(self, left_ptr, right_ptr, pitch, channels=1):
+        self._check(self.lib.vo_seq_submit(self.h, left_ptr, right_ptr, pitch, channels))
+
+    def seq_wait(self, pts_cap=4096, want_points=True):
+        res = VoUnitResult()
+        if not want_points:
+            self._check(self.lib.vo_seq_wait(self.h, C.byref(res), None, 0))
+            return self._result_dict(res)
+        pts4 = np.zeros((4, pts_cap, 2), np.float32)
+        self._check(self.lib.vo_seq_wait(self.h, C.byref(res), _p(pts4), pts_cap))
+        d = self._result_dict(res)
+        n = min(d["n_valid"], pts_cap)
+        d.update(l0=pts4[0, :n].copy(), r0=pts4[1, :n].copy(), l1=pts4[2, :n].copy(), r1=pts4[3, :n].copy())
+        return d
 
     def seq_state(self, cap=1 << 17):
         pts = np.zeros((cap, 2), np.float32); ages = np.zeros(cap, np.int32); t = np.zeros(3)

@@ -79,6 +79,10 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     vo_free_state(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& p : ctx->pending) if (p.done) cudaEventDestroy(p.done);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->seq_front_ev[k]) cudaEventDestroy(ctx->seq_front_ev[k]);
+        if (ctx->seq_back_ev[k]) cudaEventDestroy(ctx->seq_back_ev[k]);
+    }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (int c = 0; c < 2; c++) {
         if (ctx->join_ev[c]) cudaEventDestroy(ctx->join_ev[c]);
@@ -153,6 +157,8 @@ int vo_drain_pending(vo_ctx* ctx)
             VO_CUDA_CHECK(cudaEventSynchronize(p.done));
             p.active = false;
         }
+    // frames of the sequence mode still in flight on the pose-solve stream
+    if (ctx->seq_inflight > 0 && ctx->side_stream[0]) VO_CUDA_CHECK(cudaStreamSynchronize(ctx->side_stream[0]));
     return VO_OK;
 }
 
@@ -306,7 +312,7 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_feat_ages, (size_t)ctx->feat_cap));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_feat_cnt, (size_t)2));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_bucket, (size_t)ctx->bucket_cap));
-    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_seq_err, (size_t)1));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_seq_err, (size_t)4));     // [0] sticky bits, [1 + unit] per-frame copy
     ctx->seq_active = false;
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_results, 0, (size_t)units * sizeof(vo_unit_result_dev), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, (size_t)units * 3 * sizeof(double), ctx->stream));
@@ -352,7 +358,7 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
     a.cap = ctx->cap;
     a.n_pts = ctx->d_npts + v.u0;
     a.imgs_per_unit = ipu;
-    a.img_plane0 = v.u0 * ipu;
+    a.img_plane0 = v.plane0 >= 0 ? v.plane0 : v.u0 * ipu;
     a.ncalls = ncalls;
     for (int c = 0; c < ncalls; c++) { a.img_prev[c] = img_prev[c]; a.img_next[c] = img_next[c]; }
     a.nlevels = pg.nlevels;
@@ -422,7 +428,7 @@ int vo_run_fast(vo_ctx* ctx, const View& v, int plane_in_unit, bool want_resp)
     memset(&a, 0, sizeof(a));
     const size_t plane = (size_t)ctx->w * ctx->h;
     a.n_units = v.n;
-    a.img_tab = ctx->d_raw_tab + (size_t)v.u0 * ctx->imgs_per_unit + plane_in_unit;
+    a.img_tab = ctx->d_raw_tab + (size_t)(v.plane0 >= 0 ? v.plane0 : v.u0 * ctx->imgs_per_unit) + plane_in_unit;
     a.img_stride_idx = ctx->imgs_per_unit;
     a.w = ctx->w; a.h = ctx->h; a.pitch = ctx->w;
     a.threshold = ctx->p.fast_threshold; a.nonmax = ctx->p.fast_nonmax;

@@ -72,6 +72,10 @@ struct vo_ctx {
     int feat_cap = 0, bucket_cap = 4096;
     bool seq_active = false;
     int seq_slot = 0;                   // raw/pyramid planes (2*slot, 2*slot+1) hold the previous stereo pair
+    int seq_inflight = 0;               // frames submitted and not yet waited for (<= 2)
+    long long seq_submitted = 0;        // frames submitted since vo_seq_begin (frame k uses buffer unit k & 1)
+    int seq_channels[2] = {1, 1};
+    cudaEvent_t seq_front_ev[2] = {nullptr, nullptr}, seq_back_ev[2] = {nullptr, nullptr};
     long long seq_frames = 0;
     double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
     uint8_t* d_bgr = nullptr;           // staging of colour (BGR) inputs, converted by k_bgr_to_gray (ingest.cu)
@@ -116,7 +120,9 @@ int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);
 int vo_launch_bgr_to_gray(const uint8_t* d_bgr, size_t pitch, size_t img_stride_in, uint8_t* d_gray, size_t img_stride_out,
                           int w, int h, int n_img, cudaStream_t s);
 // a contiguous range of resident work units processed on one stream
-struct View { int u0, n; cudaStream_t s; };
+// plane0 >= 0 overrides the image-plane base (default u0 * imgs_per_unit): the sequence mode ping-pongs its per-frame
+// buffers between units 0 and 1 while both use the same four image planes
+struct View { int u0, n; cudaStream_t s; int plane0 = -1; };
 // run pyramids + LK (ncalls chained) for the units of `v`; images must already be in d_raw/d_raw_tab
 int vo_run_lk(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, const int* img_next, bool want_err);
 int vo_run_pyramid(vo_ctx* ctx, int plane0, int nplanes, cudaStream_t s);

@@ -52,34 +52,59 @@ __global__ void __launch_bounds__(1024) k_seq_bucket(const float2* __restrict__ 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int m = 0;
-        for (int h = 0; h <= nh; h++)
-            for (int w = 0; w <= nw; w++) {
-                const int b = bucket[h * nw + w];                        // same aliased addressing on read-back
-                if (b >= 0 && m < out_cap) { out_pts[m] = feat_pts[b]; out_ages[m] = feat_ages[b]; m++; }
-            }
-        *out_n = m;
+    // ordered read-back (same aliased addressing as the reference): cell sequence q = h * (nw + 1) + w, h <= nh, w <= nw.
+    // Each thread takes a contiguous chunk of q, a block-wide exclusive scan of the chunk counts gives its output offset.
+    __shared__ int s_cnt[1024];
+    const int per = (nb + blockDim.x - 1) / blockDim.x;
+    const int q0 = threadIdx.x * per, q1 = min(nb, q0 + per);
+    int mine = 0;
+    for (int q = q0; q < q1; q++) {
+        const int h = q / (nw + 1), w = q - h * (nw + 1);
+        mine += bucket[h * nw + w] >= 0 ? 1 : 0;
     }
+    s_cnt[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 1; d < (int)blockDim.x; d <<= 1) {           // Hillis-Steele inclusive scan
+        const int v = threadIdx.x >= d ? s_cnt[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_cnt[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int m = s_cnt[threadIdx.x] - mine;
+    for (int q = q0; q < q1; q++) {
+        const int h = q / (nw + 1), w = q - h * (nw + 1);
+        const int b = bucket[h * nw + w];
+        if (b >= 0) {
+            if (m < out_cap) { out_pts[m] = feat_pts[b]; out_ages[m] = feat_ages[b]; }
+            m++;
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1) *out_n = min(s_cnt[threadIdx.x], out_cap);
 }
 
-// after the filters and the pose solve: currentVOFeatures.points = pointsLeft_t1 (A5 survivors), the ages
-// keep their A3 length; `translation` carries the solved tvec to the next frame
-__global__ void __launch_bounds__(256) k_seq_update(const float2* __restrict__ valid_l1, const int* __restrict__ n5,
-                                                    const int* __restrict__ ages_out, const int* __restrict__ n3,
-                                                    float2* feat_pts, int* feat_ages, int* cnt,
-                                                    vo_unit_result_dev* res, double* tprev,
-                                                    const int* __restrict__ n_feat, const int* __restrict__ n_det)
+// after the circular check: currentVOFeatures.points = pointsLeft_t1 (A5 survivors), the ages keep their A3 length
+// (src/visualOdometry.cpp:122-127).  Runs before the pose solve, so the next frame's front half can start under it.
+__global__ void __launch_bounds__(256) k_seq_carry(const float2* __restrict__ valid_l1, const int* __restrict__ n5,
+                                                   const int* __restrict__ ages_out, const int* __restrict__ n3,
+                                                   float2* feat_pts, int* feat_ages, int* cnt)
 {
     const int np = *n5, na = *n3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(np, na); i += gridDim.x * blockDim.x) {
         if (i < np) feat_pts[i] = valid_l1[i];
         if (i < na) feat_ages[i] = ages_out[i];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        cnt[0] = np; cnt[1] = na;
-        for (int k = 0; k < 3; k++) tprev[k] = res->tvec[k];
-        res->n_features = *n_feat; res->n_detected = *n_det; res->n_tracked = na; res->n_valid = np;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt[0] = np; cnt[1] = na; }
+}
+
+// after the pose solve: `translation` carries the solved tvec to the next frame's solve; counts into the result record
+__global__ void k_seq_finish(vo_unit_result_dev* res, double* tprev_next, const int* __restrict__ n_feat,
+                             const int* __restrict__ n_det, const int* __restrict__ n3, const int* __restrict__ n5,
+                             const int* __restrict__ err, int* err_out)
+{
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; k++) tprev_next[k] = res->tvec[k];
+        res->n_features = *n_feat; res->n_detected = *n_det; res->n_tracked = *n3; res->n_valid = *n5;
+        *err_out = *err;
     }
 }
 
@@ -94,8 +119,13 @@ int vo_launch_seq_bucket(const SeqArgs& a, cudaStream_t s)
                                     a.out_pts, a.out_ages, a.out_n, a.out_cap, a.err);
     return 1;
 }
-int vo_launch_seq_update(const SeqArgs& a, cudaStream_t s)
+int vo_launch_seq_carry(const SeqArgs& a, cudaStream_t s)
 {
-    k_seq_update<<<8, 256, 0, s>>>(a.valid_l1, a.n5, a.ages_out, a.n3, a.feat_pts, a.feat_ages, a.cnt, a.res, a.tprev, a.out_n, a.n_det);
+    k_seq_carry<<<8, 256, 0, s>>>(a.valid_l1, a.n5, a.ages_out, a.n3, a.feat_pts, a.feat_ages, a.cnt);
+    return 1;
+}
+int vo_launch_seq_finish(const SeqArgs& a, cudaStream_t s)
+{
+    k_seq_finish<<<1, 32, 0, s>>>(a.res, a.tprev, a.out_n, a.n_det, a.n3, a.n5, a.err, a.err_out);
     return 1;
 }

@@ -12,10 +12,11 @@ struct SeqArgs {
     float2* out_pts; int* out_ages; int* out_n; int out_cap;
     // update
     const float2* valid_l1; const int* n5; const int* ages_out; const int* n3;
-    vo_unit_result_dev* res; double* tprev;
-    int* err;
+    vo_unit_result_dev* res; double* tprev /* the NEXT frame's t_prev slot */;
+    int* err; int* err_out /* per-frame copy of the sticky error bits, read back with the record */;
 };
 
 int vo_launch_seq_append(const SeqArgs& a, cudaStream_t s);
 int vo_launch_seq_bucket(const SeqArgs& a, cudaStream_t s);
-int vo_launch_seq_update(const SeqArgs& a, cudaStream_t s);
+int vo_launch_seq_carry(const SeqArgs& a, cudaStream_t s);
+int vo_launch_seq_finish(const SeqArgs& a, cudaStream_t s);
