@@ -217,10 +217,11 @@ VO_API int vo_seq_state(vo_ctx* ctx, vo_point2f* points, int32_t* ages, int cap,
  *                                 Non-interlaced PNGs of every colour type / bit depth; 16-bit -> 8-bit by the high
  *                                 byte, alpha dropped (what IMREAD_COLOR does).  Errors: vo_png_last_error().
  *   vo_reader_open                sequence_dir/image_{0,1}/%06d.png, frames first_frame .. first_frame+n_frames-1,
- *                                 `threads` decoders, `depth` (>= 2) frames of pinned ring.  force_channels: 0 = gray
+ *                                 `threads` decoders, `depth` (>= 3) frames of pinned ring.  force_channels: 0 = gray
  *                                 files are delivered as gray, colour files as BGR (device conversion); 1 / 3 force.
  *   vo_reader_next                blocks until the next frame is decoded; the returned pointers stay valid until the
- *                                 following vo_reader_next / vo_reader_close.
+ *                                 SECOND following vo_reader_next (so a frame handed to vo_seq_submit may still be
+ *                                 uploading while the next one is requested) or vo_reader_close.
  *   vo_bgr_to_gray                the device conversion on host buffers (stage-level entry point, for parity tests) */
 typedef struct vo_reader vo_reader;
 VO_API int vo_png_info(const uint8_t* file_bytes, size_t n, int* w, int* h, int* color_type, int* bit_depth);

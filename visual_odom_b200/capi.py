@@ -497,7 +497,7 @@ class SequenceReader:
         self.n_frames = n_frames
 
     def next_ptr(self):
-        """(left_ptr, right_ptr, w, h, pitch, channels, frame_id); pointers valid until the following call."""
+        """(left_ptr, right_ptr, w, h, pitch, channels, frame_id); pointers valid until the second following call."""
         l = C.c_void_p(); r = C.c_void_p(); w = C.c_int(); h = C.c_int(); p = C.c_size_t(); ch = C.c_int(); fid = C.c_int()
         rc = self.lib.vo_reader_next(self.h, C.byref(l), C.byref(r), C.byref(w), C.byref(h), C.byref(p), C.byref(ch), C.byref(fid))
         if rc != 0:

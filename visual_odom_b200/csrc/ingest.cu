@@ -219,7 +219,7 @@ struct vo_reader {
     std::mutex mu;
     std::condition_variable cv_ready, cv_free;
     int next_claim = 0;                             // next frame a worker will take
-    int consumed = 0;                               // frames handed out so far (the consumer still holds frame consumed-1)
+    int consumed = 0;                               // frames handed out so far (the consumer may still use the last two)
     bool stop = false;
     std::string error;
     std::string frame_error;
@@ -243,9 +243,12 @@ static void reader_worker(vo_reader* rd)
             std::unique_lock<std::mutex> lk(rd->mu);
             // frame i lives in slot i % depth; that slot is free once frame i - depth has been released, i.e. the
             // consumer has moved past it: it holds frame consumed-1 at most.
+            // frame i lives in slot i % depth.  The consumer may still be using the last TWO frames it was handed
+            // (frames consumed-1 and consumed-2: one being uploaded asynchronously while the next is requested), so
+            // slot reuse needs i - depth < consumed - 2.
             rd->cv_free.wait(lk, [&] {
-                const int held_from = rd->consumed > 0 ? rd->consumed : 1;
-                return rd->stop || rd->next_claim >= rd->count || rd->next_claim < held_from + rd->depth - 1;
+                const int c = rd->consumed > 2 ? rd->consumed : 2;
+                return rd->stop || rd->next_claim >= rd->count || rd->next_claim < c + rd->depth - 2;
             });
             if (rd->stop || rd->next_claim >= rd->count) return;
             i = rd->next_claim++;
@@ -277,7 +280,7 @@ extern "C" vo_reader* vo_reader_open(const char* sequence_dir, int first_frame, 
     g_png_err.clear();
     if (!sequence_dir || n_frames <= 0 || first_frame < 0) { g_png_err = "vo_reader_open: bad argument"; return nullptr; }
     if (threads <= 0) threads = 4;
-    if (depth < 2) depth = 2;
+    if (depth < 3) depth = 3;
     vo_reader* rd = new vo_reader();
     rd->dir = sequence_dir; rd->first = first_frame; rd->count = n_frames; rd->depth = depth;
     std::vector<uint8_t> file;
@@ -307,7 +310,7 @@ extern "C" int vo_reader_next(vo_reader* rd, const uint8_t** left, const uint8_t
     std::unique_lock<std::mutex> lk(rd->mu);
     if (rd->consumed >= rd->count) { rd->error = "vo_reader_next: end of sequence"; return VO_E_INVALID; }
     const int i = rd->consumed;
-    rd->consumed++;                                 // releases the slot of frame i-1 (handed out by the previous call)
+    rd->consumed++;                                 // releases the slot of frame i-2
     rd->cv_free.notify_all();
     rd->cv_ready.wait(lk, [&] { return rd->state[i] != 0; });
     if (rd->state[i] < 0) { rd->error = rd->frame_error; return VO_E_INVALID; }
