@@ -246,7 +246,7 @@ def sequence_mode(ctx, torch, cal, n_frames):
             cv2.imwrite(os.path.join(d, "image_1", "%06d.png" % i), r)
         threads = max(2, min(16, len(os.sched_getaffinity(0)) // 2))
         for rep in range(2):
-            rd = capi.SequenceReader(d, 0, n_frames + 1, threads=threads, depth=4)
+            rd = capi.SequenceReader(d, 0, n_frames + 1, threads=threads, depth=threads + 3)
             t0 = time.perf_counter()
             lp, rp, rw, rh, rpitch, ch, fid = rd.next_ptr()
             ctx.seq_begin_ptr(rw, rh, lp, rp, rpitch, base["P_l"], base["P_r"], ch)
@@ -265,7 +265,7 @@ def sequence_mode(ctx, torch, cal, n_frames):
                 cv2.cvtColor(cv2.imread(os.path.join(d, "image_%d" % cam, "%06d.png" % i), cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY)
         cpu_load_ms = 1e3 * (time.perf_counter() - t0) / min(n_frames + 1, 13)
         shutil.rmtree(d, ignore_errors=True)
-        png = {"value": n_frames / dt_png, "unit": "frames/s", "decode_threads": threads, "ring_depth": 4,
+        png = {"value": n_frames / dt_png, "unit": "frames/s", "decode_threads": threads, "ring_depth": threads + 3,
                "same_result_as_memory_path": bool(got_f["n_inliers"] == got["n_inliers"] and np.array_equal(got_f["tvec"], got["tvec"])),
                "cpu_imread_cvtcolor_ms_per_frame_pair": cpu_load_ms,
                "note": "PNG files -> vo_reader (decode ahead, pinned ring) -> vo_seq_submit / vo_seq_wait; includes vo_seq_begin"}
