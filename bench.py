@@ -503,7 +503,11 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cpu_best = cpu_reference_best(units, args, args.cpu_sample)
+        if world == 1:
+            cpu_best = cpu_reference_best(units, args, args.cpu_sample)
+        else:                                    # the host baseline is an N = 1 measurement (see --impl reference)
+            cpu_best = {"value": None, "seconds": 0.0, "cores": 0, "frames": 0, "how": "not measured at N > 1", "tried": [],
+                        "affinity_cores": len(os.sched_getaffinity(0))}
         cpu_fps, cpu_dt, cores = cpu_best["value"], cpu_best["seconds"], cpu_best["cores"]
         seq = None
         if world == 1 and args.sequence > 0:
