@@ -2,9 +2,9 @@
 # tools/sweep.sh -- BASELINE.json configs 3 and 5 on one GPU: feature-count sweep at 1241x376 and the 1920x1080 / 4000-feature case.
 mkdir -p gpurun_out
 for n in 500 1000 2000 4000 8000; do
-  timeout 300 python bench.py --features $n --steps 10 --warmup 3 --cpu-sample 2 2>/dev/null | tail -1 > gpurun_out/sweep_n$n.json
+  timeout 300 python bench.py --features $n --steps 40 --warmup 3 --cpu-sample 2 --sequence 0 2>/dev/null | tail -1 > gpurun_out/sweep_n$n.json
 done
-timeout 400 python bench.py --width 1920 --height 1080 --calib zed --features 4000 --units 4 --steps 6 --warmup 2 --cpu-sample 2 2>/dev/null | tail -1 > gpurun_out/sweep_1080p_n4000.json
+timeout 400 python bench.py --width 1920 --height 1080 --calib zed --features 4000 --units 4 --steps 20 --warmup 3 --cpu-sample 2 --sequence 0 2>/dev/null | tail -1 > gpurun_out/sweep_1080p_n4000.json
 python - <<'PY'
 import json,glob
 rows=[]
