@@ -316,8 +316,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     unsigned d00 = dw[0], d01 = dw[1];
 #pragma unroll
                     for (int k = 0; k < ne; k++) {
-                        const unsigned pbot = __funnelshift_r(iw[(k + 1) * (IW / 4)], iw[(k + 1) * (IW / 4) + 1], ish);
-                        const unsigned d10 = dw[(k + 1) * DW], d11 = dw[(k + 1) * DW + 1];
+                        // the padding element of a short strip / segment would read one row past the windows: skip its loads
+                        const bool live = k < nvalid || (part && !has_tail);
+                        const unsigned pbot = live ? __funnelshift_r(iw[(k + 1) * (IW / 4)], iw[(k + 1) * (IW / 4) + 1], ish) : 0u;
+                        const unsigned d10 = live ? dw[(k + 1) * DW] : 0u, d11 = live ? dw[(k + 1) * DW + 1] : 0u;
                         const int ival = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5));
                         int ix = ((int)(short)(d00 & 0xffff) * w00 + (int)(short)(d01 & 0xffff) * w01 +
                                   (int)(short)(d10 & 0xffff) * w10 + (int)(short)(d11 & 0xffff) * w11 + (1 << (W_BITS - 1))) >> W_BITS;
@@ -392,14 +394,15 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 unsigned axs = 0, ays = 0, axt = 0, ayt = 0;    // sums of |addend|
 #pragma unroll
                 for (int part = 0; part < 2; part++) {
-                    const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11;
+                    const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11, nvalid = part ? tn : (half ? 10 : 11);
                     const int joff = (ry + row0) * IW + rx + c0;
                     const uint32_t* jw = reinterpret_cast<const uint32_t*>(sm.jtile) + (joff >> 2);
                     const int jsh = 8 * (joff & 3);
                     unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
 #pragma unroll
                     for (int k = 0; k < ne; k++) {
-                        const unsigned pbot = __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh);
+                        const bool live = k < nvalid || (part && !has_tail);        // see the patch extraction
+                        const unsigned pbot = live ? __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh) : 0u;
                         const int e = part ? 11 + k : k;
                         const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
                         const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
@@ -507,7 +510,8 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         unsigned ptop = __funnelshift_r(jw[0], jw[1], jsh);
 #pragma unroll
                         for (int k = 0; k < ne; k++) {
-                            const unsigned pbot = __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh);
+                            const bool live = k < nvalid || (part && !has_tail);
+                            const unsigned pbot = live ? __funnelshift_r(jw[(k + 1) * (IW / 4)], jw[(k + 1) * (IW / 4) + 1], jsh) : 0u;
                             const int e = part ? 11 + k : k;
                             const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
                             const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
