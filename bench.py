@@ -83,6 +83,9 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter() + 0.5          # a very short timed region: wait for the first sample (clocks are still up)
+        while not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
         self.proc.terminate()          # exact PID we started
         try:
             self.proc.wait(timeout=5)
