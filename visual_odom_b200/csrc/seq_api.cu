@@ -9,12 +9,14 @@
 // Only the back stage of frame k+1 needs the back stage of frame k (the extrinsic guess), so vo_seq_submit may be called
 // for frame k+1 before vo_seq_wait returned frame k: its front stage then runs under the latency-bound pose solve of
 // frame k.  Per-frame device buffers are the batch state's unit slots k & 1 (two frames in flight at most); the
-// sequence state proper (FeatureSet, the four image planes + pyramids, translation) is shared.  Each stage is one CUDA
-// graph (per image-slot parity / buffer unit / input format).
+// sequence state proper (FeatureSet, the image planes + pyramids, translation) is shared.  The stereo pairs live in a
+// ring of THREE image slots (6 planes): gray uploads go through a copy stream into the slot that neither the running
+// nor the previous frame reads, so the H2D of frame k+1 also runs under the kernels of frame k (double-buffered
+// upload).  Each stage is one CUDA graph (per image-slot pair / buffer unit / input format).
 #include "ctx.h"
 #include <string.h>
 
-static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t* right, size_t pitch, int channels)
+static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t* right, size_t pitch, int channels, cudaStream_t st)
 {
     const int w = ctx->w, h = ctx->h;
     const uint8_t* imgs[2] = {left, right};
@@ -23,13 +25,13 @@ static int upload_pair(vo_ctx* ctx, int slot, const uint8_t* left, const uint8_t
         int rc = vo_ensure_bgr(ctx, 2 * img);
         if (rc) return rc;
         for (int k = 0; k < 2; k++)
-            VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_bgr + k * img, (size_t)3 * w, imgs[k], pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+            VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_bgr + k * img, (size_t)3 * w, imgs[k], pitch, (size_t)3 * w, h, cudaMemcpyHostToDevice, st));
         return VO_OK;
     }
     for (int k = 0; k < 2; k++) {
         uint8_t* dst = ctx->d_raw + (size_t)(2 * slot + k) * w * h;
-        if (pitch == (size_t)w) VO_CUDA_CHECK(cudaMemcpyAsync(dst, imgs[k], (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
-        else VO_CUDA_CHECK(cudaMemcpy2DAsync(dst, w, imgs[k], pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+        if (pitch == (size_t)w) VO_CUDA_CHECK(cudaMemcpyAsync(dst, imgs[k], (size_t)w * h, cudaMemcpyHostToDevice, st));
+        else VO_CUDA_CHECK(cudaMemcpy2DAsync(dst, w, imgs[k], pitch, w, h, cudaMemcpyHostToDevice, st));
     }
     return VO_OK;
 }
@@ -60,13 +62,12 @@ static void seq_args(vo_ctx* ctx, int unit, SeqArgs& a)
     a.err = ctx->d_seq_err; a.err_out = ctx->d_seq_err + 1 + unit;
 }
 
-// front stage of one frame on the caller's stream; s0 = image slot of the previous pair, unit = per-frame buffer slot
-static int seq_front(vo_ctx* ctx, int s0, int unit, bool bgr)
+// front stage of one frame on the caller's stream; s0 / s1 = image slots of the previous / new pair, unit = per-frame buffers
+static int seq_front(vo_ctx* ctx, int s0, int s1, int unit, bool bgr)
 {
     ctx->imgs_per_unit = 4;
-    const int s1 = 1 - s0;
     const int L0 = 2 * s0, R0 = 2 * s0 + 1, L1 = 2 * s1, R1 = 2 * s1 + 1;
-    const View v{unit, 1, ctx->stream, 0};                    // image planes are 0..3 whatever the buffer unit
+    const View v{unit, 1, ctx->stream, 0};                    // image planes are 0..5 whatever the buffer unit
     int rc;
     if (bgr && (rc = convert_pair(ctx, s1))) return rc;
     // the new pair's two pyramids (the previous pair's are already resident)
@@ -195,7 +196,7 @@ extern "C" int vo_seq_begin_ex(vo_ctx* ctx, int w, int h, const float P_l[12], c
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_feat_cnt, 0, 2 * sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_seq_err, 0, 4 * sizeof(int), ctx->stream));
     VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_tprev, 0, 6 * sizeof(double), ctx->stream));      // translation = zeros (main.cpp:82)
-    if ((rc = upload_pair(ctx, 0, left0, right0, pitch, channels))) return rc;
+    if ((rc = upload_pair(ctx, 0, left0, right0, pitch, channels, ctx->stream))) return rc;
     if (channels == 3 && (rc = convert_pair(ctx, 0))) return rc;
     if ((rc = vo_run_pyramid(ctx, 0, 2, ctx->stream))) return rc;
     // both event pairs start out signalled, so the first two frames do not wait for a predecessor
@@ -217,13 +218,27 @@ extern "C" int vo_seq_submit(vo_ctx* ctx, const uint8_t* left1, const uint8_t* r
     if (ctx->seq_inflight >= 2) { vo_set_error(ctx, "vo_seq_submit: two frames are in flight already; call vo_seq_wait"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     const int unit = (int)(ctx->seq_submitted & 1);
-    const int s0 = ctx->seq_slot, s1 = 1 - s0;
+    const int s0 = ctx->seq_slot, s1 = (s0 + 1) % 3;
+    const bool bgr = channels == 3;
     int rc;
     // the per-frame buffers of `unit` were last read by the back stage of frame k-2
     VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->seq_back_ev[unit], 0));
-    if ((rc = upload_pair(ctx, s1, left1, right1, pitch, channels))) return rc;
-    const bool bgr = channels == 3;
-    if ((rc = seq_graph(ctx, -1 - (s0 + 2 * unit + 4 * (bgr ? 1 : 0)), ctx->stream, [&] { return seq_front(ctx, s0, unit, bgr); }))) return rc;
+    if (bgr) {
+        // colour frames share one staging buffer: upload + convert stay on the front stream
+        if ((rc = upload_pair(ctx, s1, left1, right1, pitch, channels, ctx->stream))) return rc;
+    } else {
+        // image slot s1 (of three) was last read, as the previous pair, by the front stage of the frame before the one
+        // now running: that frame has this frame's buffer parity, and its seq_front_ev[unit] record is still the
+        // current one (it is re-recorded below).  So this copy runs under the front stage of the frame in flight.
+        // (No ordering against the caller's stream is needed: vo_seq_begin synchronises, and every later access to
+        // the image slots is made by this file and ordered through these events.)
+        cudaStream_t sc = ctx->side_stream[1];
+        VO_CUDA_CHECK(cudaStreamWaitEvent(sc, ctx->seq_front_ev[unit], 0));
+        if ((rc = upload_pair(ctx, s1, left1, right1, pitch, channels, sc))) return rc;
+        VO_CUDA_CHECK(cudaEventRecord(ctx->join_ev[1], sc));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[1], 0));
+    }
+    if ((rc = seq_graph(ctx, -1 - (s0 + 3 * unit + 6 * (bgr ? 1 : 0)), ctx->stream, [&] { return seq_front(ctx, s0, s1, unit, bgr); }))) return rc;
     VO_CUDA_CHECK(cudaEventRecord(ctx->seq_front_ev[unit], ctx->stream));
     // back stage: after this frame's front stage; after the previous frame's back stage by stream order
     cudaStream_t sb = ctx->side_stream[0];
