@@ -77,8 +77,11 @@ VO_API long long vo_kernel_launches(const vo_ctx* ctx);
  * measured with CUDA events on the launching stream; n = launches counted. */
 VO_API int vo_lk_kernel_time(vo_ctx* ctx, double* ms_total, long long* n, int reset);
 /* Run-time knobs (measurement / debugging): "batch_streams" = 1|2 (unit ranges the batched path runs
- * concurrently, default 2), "lk_staging" = 0 (TMA, default) | 1 (plain loads), "graphs" = 1 (default: the
- * batched path replays its kernel sequence as CUDA graphs) | 0 (plain launches; needed for vo_lk_kernel_time). */
+ * concurrently, default 2), "lk_staging" = 0 (TMA, default) | 1 (plain loads), "graphs" = 1 (default: kernel
+ * sequences are replayed as CUDA graphs where that does not defeat the priority split) | 0 (plain launches; needed
+ * for vo_lk_kernel_time), "priorities" = 1 (default: with several unit ranges in flight the short / latency-bound
+ * kernels run on high-priority helper streams and only the LK ring at normal priority; such ranges are launched
+ * plainly because captured graph nodes lose the stream priority) | 0, "batch_graphs" = 1 forces graphs for them. */
 VO_API int vo_set_option(vo_ctx* ctx, const char* key, double value);
 
 /* ---- A1: cv::FAST(image, kps, threshold, nonmax) + KeyPoint::convert ------------------------

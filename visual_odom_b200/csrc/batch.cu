@@ -116,26 +116,66 @@ static int ensure_side_streams(vo_ctx* ctx)
     return VO_OK;
 }
 
-// the whole path for the resident units of `v`, asynchronous on v.s
+// high-priority helper streams: the short and the latency-bound kernels of a range (FAST, pyramids, filters,
+// triangulation, PnP) are issued there, the LK ring at normal priority.  With two ranges in flight the helpers' few
+// CTAs are then never queued behind the thousands of pending CTAs of the OTHER range's LK launch, so consecutive LK
+// launches follow each other directly and the ramp-down of one (a feature-ring lasts ~0.3 ms) fills with the next.
+static int ensure_hi_streams(vo_ctx* ctx)
+{
+    if (ctx->hi_stream[0]) return VO_OK;
+    int lo = 0, hi = 0;
+    VO_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi is the numerically smallest value
+    for (int c = 0; c < 2; c++) {
+        VO_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->hi_stream[c], cudaStreamNonBlocking, hi));
+        for (int k = 0; k < 4; k++) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->hi_ev[c][k], cudaEventDisableTiming));
+    }
+    return VO_OK;
+}
+
+// the whole path for the resident units of `v`, asynchronous on v.s.  When v.s is one of the side streams and
+// priorities are enabled, everything but the LK ring is forked to that side stream's high-priority helper.
 static int run_range_launch(vo_ctx* ctx, const View& v)
 {
     ctx->imgs_per_unit = 4;
     int rc;
+    int c = -1;
+    if (ctx->use_priorities)
+        for (int k = 0; k < 2; k++) if (ctx->side_stream[k] && v.s == ctx->side_stream[k]) c = k;
+    View h = v;                                  // the view the helper kernels run on
+    if (c >= 0) {
+        if ((rc = ensure_hi_streams(ctx))) return rc;
+        h.s = ctx->hi_stream[c];
+        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][0], v.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ctx->hi_ev[c][0], 0));
+    }
     if (ctx->batch_detect) {
-        if ((rc = vo_run_fast(ctx, v, 0, false))) return rc;
-        if ((rc = vo_run_select(ctx, v))) return rc;
+        if ((rc = vo_run_fast(ctx, h, 0, false))) return rc;
+        if ((rc = vo_run_select(ctx, h))) return rc;
+    }
+    if ((rc = vo_run_pyramid(ctx, v.u0 * ctx->imgs_per_unit, v.n * ctx->imgs_per_unit, h.s))) return rc;
+    if (c >= 0) {
+        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][1], h.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ctx->hi_ev[c][1], 0));
     }
     const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};      // ring L0->R0->R1->L1->L0 (planes L0,R0,L1,R1)
-    if ((rc = vo_run_lk(ctx, v, 4, ip, in, false))) return rc;
-    if ((rc = vo_run_filter(ctx, v, false))) return rc;
+    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
+    if (c >= 0) {
+        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][2], v.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ctx->hi_ev[c][2], 0));
+    }
+    if ((rc = vo_run_filter(ctx, h, false))) return rc;
     const size_t cs = (size_t)ctx->units * ctx->cap;
-    if ((rc = vo_run_triangulate(ctx, v, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
+    if ((rc = vo_run_triangulate(ctx, h, ctx->d_valid4, ctx->d_valid4 + cs, ctx->d_n5))) return rc;
     float K9[9] = {ctx->P_l[0], ctx->P_l[1], ctx->P_l[2], ctx->P_l[4], ctx->P_l[5], ctx->P_l[6], ctx->P_l[8], ctx->P_l[9], ctx->P_l[10]};
-    if ((rc = vo_run_pnp(ctx, v, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
-    k_pack_counts<<<(v.n + 63) / 64, 64, 0, v.s>>>(ctx->d_results + v.u0, ctx->d_npts + v.u0, ctx->d_ndet + v.u0, ctx->d_n3 + v.u0,
+    if ((rc = vo_run_pnp(ctx, h, ctx->d_valid4 + 2 * cs, ctx->d_n5, K9))) return rc;
+    k_pack_counts<<<(v.n + 63) / 64, 64, 0, h.s>>>(ctx->d_results + v.u0, ctx->d_npts + v.u0, ctx->d_ndet + v.u0, ctx->d_n3 + v.u0,
                                                   ctx->d_n5 + v.u0, v.n, ctx->batch_detect ? 1 : 0);
     ctx->launches += 1;
     VO_CUDA_CHECK(cudaGetLastError());
+    if (c >= 0) {                                // join: later work on v.s (result copy, the next submission) sees everything
+        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][3], h.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ctx->hi_ev[c][3], 0));
+    }
     return VO_OK;
 }
 
@@ -144,7 +184,12 @@ static int run_range_launch(vo_ctx* ctx, const View& v)
 // the device state is re-allocated.  The LK event timing is not part of graphs.
 static int run_range(vo_ctx* ctx, const View& v)
 {
-    if (!ctx->use_graphs) return run_range_launch(ctx, v);
+    // Kernel nodes of a captured graph do not keep the capture streams' priorities (measured: no effect), and the
+    // priority split is worth more (+7 % on the pipelined step) than the graph's launch savings (+2 %): ranges that run
+    // on a side stream with priorities enabled are launched plainly unless "batch_graphs" forces graphs.
+    bool on_side = false;
+    for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
+    if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
         if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));

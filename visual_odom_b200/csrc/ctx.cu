@@ -87,6 +87,8 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     for (int c = 0; c < 2; c++) {
         if (ctx->join_ev[c]) cudaEventDestroy(ctx->join_ev[c]);
         if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
+        if (ctx->hi_stream[c]) cudaStreamDestroy(ctx->hi_stream[c]);
+        for (int k = 0; k < 4; k++) if (ctx->hi_ev[c][k]) cudaEventDestroy(ctx->hi_ev[c][k]);
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_bgr) cudaFree(ctx->d_bgr);
@@ -117,6 +119,8 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (strcmp(key, "batch_streams") == 0) { ctx->batch_streams = value >= 2 ? 2 : 1; return VO_OK; }
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
     if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
+    if (strcmp(key, "batch_graphs") == 0) { ctx->batch_graphs = value >= 1; return VO_OK; }
+    if (strcmp(key, "priorities") == 0) { ctx->use_priorities = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
     vo_set_error(ctx, "unknown option %s", key);
     return VO_E_INVALID;
 }

@@ -103,6 +103,10 @@ struct vo_ctx {
     struct RangeGraph { int u0, n; bool detect, tma; cudaGraphExec_t exec; long long launches; };
     std::vector<RangeGraph> graphs; // invalidated when the device state is re-allocated
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
+    cudaStream_t hi_stream[2] = {nullptr, nullptr};     // high-priority helpers of the side streams (see run_range_launch)
+    cudaEvent_t hi_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    bool use_priorities = true;
+    bool batch_graphs = false;      // force CUDA graphs for side-stream ranges even though they lose the priority split
     cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     struct Pending { int u0 = 0, n = 0; bool active = false; cudaEvent_t done = nullptr; };
