@@ -185,3 +185,29 @@ def test_facade_load_image_left_right(tmp_path):
         assert np.array_equal(col, ref) and np.array_equal(gray, cv2.cvtColor(ref, cv2.COLOR_BGR2GRAY))
     r = subprocess.run([exe, "load", str(tmp_path) + "/", "8", str(out)], capture_output=True, text=True)
     assert r.returncode == 6 and "cannot open" in r.stderr
+
+
+@pytest.mark.parametrize("threads,depth", [(1, 3), (8, 3), (8, 16), (3, 5)])
+def test_reader_ring_under_pressure(tmp_path, threads, depth):
+    """More decoders than ring slots, a consumer that holds two frames (the contract vo_seq_submit relies on): frames come
+    back in order, the two most recent hand-outs stay intact while later frames are being decoded, early close joins."""
+    import ctypes as C
+    rng = np.random.default_rng(threads * 100 + depth)
+    n = 40
+    frames = [(rng.integers(0, 256, (48, 64), dtype=np.uint8), rng.integers(0, 256, (48, 64), dtype=np.uint8)) for _ in range(n)]
+    _write_sequence(str(tmp_path), frames)
+    rd = capi.SequenceReader(str(tmp_path), 0, n, threads=threads, depth=depth)
+    held = []
+    for i in range(n):
+        l, r, w, h, pitch, ch, fid = rd.next_ptr()
+        assert (w, h, ch, fid) == (64, 48, 1, i)
+        held.append((i, l, r))
+        held = held[-2:]                                   # the consumer keeps using the last two hand-outs
+        for j, lp, rp in held:
+            la = np.ctypeslib.as_array((C.c_uint8 * (48 * 64)).from_address(lp)).reshape(48, 64)
+            ra = np.ctypeslib.as_array((C.c_uint8 * (48 * 64)).from_address(rp)).reshape(48, 64)
+            assert np.array_equal(la, frames[j][0]) and np.array_equal(ra, frames[j][1]), (i, j)
+    rd.close()
+    rd = capi.SequenceReader(str(tmp_path), 0, n, threads=threads, depth=depth)      # close with work outstanding
+    rd.next_ptr()
+    rd.close()
