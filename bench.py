@@ -385,7 +385,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    for opt in ("graphs", "priorities", "batch_graphs", "graph_node_priorities"):   # A/B switches for experiments, e.g. VO_OPT_PRIORITIES=0 VO_OPT_BATCH_GRAPHS=1
+    for opt in ("graphs", "priorities", "batch_graphs"):   # A/B switches for experiments, e.g. VO_OPT_PRIORITIES=0 VO_OPT_BATCH_GRAPHS=1
         if os.environ.get("VO_OPT_" + opt.upper()) is not None:
             ctx.set_option(opt, float(os.environ["VO_OPT_" + opt.upper()]))
     ctx.batch_configure(W_IMG, H_IMG, 2 * B, units[0]["P_l"], units[0]["P_r"])     # two slot ranges of B (pipelined e2e)

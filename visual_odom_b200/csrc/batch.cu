@@ -6,8 +6,6 @@
 // i.e. reference src/visualOdometry.cpp:81-129 (matchingFeatures, with the bucketing replaced by
 // the benchmark's stride selection), src/main.cpp:170-171 and src/visualOdometry.cpp:132-193.
 #include "ctx.h"
-#include "lk_ring.h"
-#include <vector>
 #include <string.h>
 
 __global__ void k_pack_counts(vo_unit_result_dev* res, const int* n_pts, const int* n_det, const int* n3, const int* n5,
@@ -191,7 +189,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     // on a side stream with priorities enabled are launched plainly unless "batch_graphs" forces graphs.
     bool on_side = false;
     for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
-    if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs && !ctx->graph_node_prio)) return run_range_launch(ctx, v);
+    if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
         if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));
@@ -211,27 +209,6 @@ static int run_range(vo_ctx* ctx, const View& v)
     vo_ctx::RangeGraph g;
     g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma;
     g.launches = ctx->launches - before;
-    if (ctx->graph_node_prio && ctx->use_priorities && on_side) {
-        // EXPERIMENTAL, off by default (option "graph_node_priorities"): give every kernel node but the LK ring the
-        // highest priority explicitly, to keep the priority split inside a graph.  Best effort: errors are ignored.
-        int lo = 0, hi = 0;
-        size_t nn = 0;
-        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess && nn) {
-            std::vector<cudaGraphNode_t> nodes(nn);
-            if (cudaGraphGetNodes(graph, nodes.data(), &nn) == cudaSuccess)
-                for (size_t i = 0; i < nn; i++) {
-                    cudaGraphNodeType ty;
-                    cudaKernelNodeParams kp;
-                    if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
-                    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
-                    cudaKernelNodeAttrValue val;
-                    memset(&val, 0, sizeof(val));
-                    val.priority = kp.func == vo_lk_kernel_func() ? lo : hi;
-                    cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &val);
-                }
-        }
-        cudaGetLastError();
-    }
     VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
     ctx->graphs.push_back(g);

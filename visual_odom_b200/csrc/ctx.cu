@@ -119,7 +119,6 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (strcmp(key, "batch_streams") == 0) { ctx->batch_streams = value >= 2 ? 2 : 1; return VO_OK; }
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
     if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
-    if (strcmp(key, "graph_node_priorities") == 0) { ctx->graph_node_prio = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "batch_graphs") == 0) { ctx->batch_graphs = value >= 1; return VO_OK; }
     if (strcmp(key, "priorities") == 0) { ctx->use_priorities = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
     vo_set_error(ctx, "unknown option %s", key);

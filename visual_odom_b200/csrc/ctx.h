@@ -107,7 +107,6 @@ struct vo_ctx {
     cudaEvent_t hi_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     bool use_priorities = true;
     bool batch_graphs = false;      // force CUDA graphs for side-stream ranges even though they lose the priority split
-    bool graph_node_prio = false;   // EXPERIMENTAL (untested on hardware, off): graphs + explicit per-node priorities
     cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     struct Pending { int u0 = 0, n = 0; bool active = false; cudaEvent_t done = nullptr; };

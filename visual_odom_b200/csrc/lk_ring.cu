@@ -543,8 +543,6 @@ cudaError_t vo_lk_prepare()
     return cudaFuncSetAttribute(k_lk_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vo_lk_smem_bytes());
 }
 
-const void* vo_lk_kernel_func() { return (const void*)k_lk_ring; }
-
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, cudaStream_t stream)
 {
     const long warps = (long)args.n_units * args.cap;

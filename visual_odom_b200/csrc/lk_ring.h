@@ -41,5 +41,4 @@ struct LkArgs {
 size_t vo_lk_smem_bytes();
 cudaError_t vo_lk_prepare();
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
-const void* vo_lk_kernel_func();       // identifies the LK kernel node inside a captured graph
 int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch, cudaStream_t stream);
