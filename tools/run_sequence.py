@@ -84,7 +84,10 @@ def main():
     if a.gt:
         gt = capi.poses_load(a.gt)[a.first:a.first + n]
         seg, t_err, r_err = capi.eval_segments(gt, poses[:len(gt)])
-        print(f"KITTI metric over {len(seg)} segments: t_err {100 * t_err:.2f} %, r_err {r_err * 180 / np.pi * 100:.4f} deg / 100 m")
+        if len(seg) == 0:
+            print("KITTI metric: the ground-truth path is shorter than the 100 m minimum segment, nothing to score")
+        else:
+            print(f"KITTI metric over {len(seg)} segments: t_err {100 * t_err:.2f} %, r_err {r_err * 180 / np.pi * 100:.4f} deg / 100 m")
 
 
 if __name__ == "__main__":
