@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--units", type=int, default=8, help="independent stereo pairs per step per GPU")
     ap.add_argument("--features", type=int, default=N_FEAT)
-    ap.add_argument("--cpu-sample", type=int, default=400, help="frames timed for cpu_baseline (~10 s of host work)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="timed host work per CPU mode (sequential / process pool), in 3 repetitions")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="(ignored; kept for old command lines)")
+    ap.add_argument("--sweep", type=int, default=1, help="N = 1: also run the feature sweep / 1080p / single-pair / sequence points (0 = headline only)")
     ap.add_argument("--sequence", type=int, default=48,
                     help="frames of the streaming-mode (vo_seq_push) side measurement at N=1; 0 = skip")
     ap.add_argument("--width", type=int, default=W_IMG)
@@ -174,26 +176,87 @@ def cpu_reference_parallel(n_proc, w, h, calib, n_feat, frames, threads_per_proc
     return done / dt, dt, done
 
 
-def cpu_reference_best(units, args, frames):
-    """The better of (a) sequential frames with OpenCV's internal threads and (b) one process per core group."""
+def _median(xs):
+    return float(np.median(np.asarray(xs, np.float64)))
+
+
+def cpu_reference_measure(units, args, seconds_per_mode=10.0, reps=3):
+    """The reference's CPU path on this host, both ways, each for >= `seconds_per_mode` of timed work in `reps`
+    repetitions (median / min / max reported):
+      sequential -- one frame after the other, OpenCV's own thread pool inside every call: how the reference's ./run
+                    executes (src/main.cpp:123-224 is a serial loop);
+      pool       -- independent work units on a process pool, one OpenCV thread per process; the number of busy
+                    workers is chosen from a measured scaling curve (quarter / half / all of the affinity cores), not fixed.
+    The headline CPU figure is the better median of the two."""
+    import cv2
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    fps_a, dt_a, cv_threads = cpu_reference_frames(units, args.features, frames)
-    best = {"value": fps_a, "cores": cv_threads, "seconds": dt_a, "frames": frames,
-            "how": f"sequential frames, {cv_threads} OpenCV threads (cv2 default)"}
-    tried = [f"sequential x{cv_threads} threads: {fps_a:.1f} fps"]
+    out = {"affinity_cores": cores, "cv2": cv2.__version__}
+    # ---- sequential -------------------------------------------------------------------------------------------
+    cv2.setNumThreads(-1)
+    for i in range(min(3, len(units))):
+        _cpu_one_frame(units[i], args.features)
+    fps, frames_seq = [], 0
+    t_seq = 0.0
+    for r in range(reps):                       # time-based repetitions: whole frames until the repetition's share has passed
+        n, t0 = 0, time.perf_counter()
+        while True:
+            _cpu_one_frame(units[n % len(units)], args.features)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt >= seconds_per_mode / reps and n >= 2:
+                break
+        t_seq += dt
+        frames_seq += n
+        fps.append(n / dt)
+    per_rep = frames_seq // reps
+    out["sequential"] = {"median": _median(fps), "min": min(fps), "max": max(fps), "opencv_threads": cv2.getNumThreads(),
+                         "frames_per_rep": per_rep, "reps": reps, "seconds": t_seq}
+    # ---- process pool -----------------------------------------------------------------------------------------
     try:
-        n_proc = max(1, min(cores, 64))
-        per = max(1, cores // n_proc)
-        fps_b, dt_b, done = cpu_reference_parallel(n_proc, W_IMG, H_IMG, args.calib, args.features, max(frames, 4 * n_proc), per)
-        tried.append(f"{n_proc} processes x{per} threads: {fps_b:.1f} fps")
-        if fps_b > best["value"]:
-            best = {"value": fps_b, "cores": n_proc * per, "seconds": dt_b, "frames": done,
-                    "how": f"{n_proc} processes x {per} OpenCV thread(s), independent work units, {done} frames"}
+        import multiprocessing as mp
+        n_proc = max(1, min(cores, 128))
+        ctxm = mp.get_context("spawn")                 # no fork: OpenCV's thread pool does not survive one
+        with ctxm.Pool(n_proc, initializer=_pool_init, initargs=(W_IMG, H_IMG, args.calib, args.features, 1)) as pool:
+            pool.map(_pool_run, [1] * (2 * n_proc), chunksize=1)          # every worker initialised and warm
+            curve = {}
+            for k in sorted({max(1, n_proc // 4), max(1, n_proc // 2), n_proc}):
+                t0 = time.perf_counter()
+                done = sum(pool.map(_pool_run, [2] * k, chunksize=1))     # k tasks -> k busy workers
+                curve[k] = done / (time.perf_counter() - t0)
+            k_best = max(curve, key=curve.get)
+            chunk = max(2, int(np.ceil(curve[k_best] * seconds_per_mode / reps / k_best)))
+            fps = []
+            t_pool = 0.0
+            for r in range(reps):
+                t0 = time.perf_counter()
+                done = sum(pool.map(_pool_run, [chunk] * k_best, chunksize=1))
+                dt = time.perf_counter() - t0
+                t_pool += dt
+                fps.append(done / dt)
+        out["pool"] = {"median": _median(fps), "min": min(fps), "max": max(fps), "busy_workers": k_best, "opencv_threads_per_worker": 1,
+                       "frames_per_rep": chunk * k_best, "reps": reps, "seconds": t_pool,
+                       "scaling_curve_fps": {str(k): round(v, 1) for k, v in curve.items()}}
     except Exception as e:                       # never lose the line to the pool
-        tried.append(f"process pool failed: {str(e)[:80]}")
-    best["tried"] = tried
-    best["affinity_cores"] = cores
-    return best
+        out["pool"] = {"error": str(e)[:160]}
+    seq_med = out["sequential"]["median"]
+    pool_med = out["pool"].get("median", 0.0)
+    if pool_med > seq_med:
+        out["best"] = {"value": pool_med, "mode": "pool", "cores": out["pool"]["busy_workers"], "seconds": out["pool"]["seconds"],
+                       "frames": out["pool"]["frames_per_rep"] * reps, "spread": [out["pool"]["min"], out["pool"]["max"]]}
+    else:
+        out["best"] = {"value": seq_med, "mode": "sequential", "cores": out["sequential"]["opencv_threads"], "seconds": t_seq,
+                       "frames": frames_seq, "spread": [out["sequential"]["min"], out["sequential"]["max"]]}
+    return out
+
+
+def cpu_sample_text(m):
+    b = m["best"]
+    return (f"{b['frames']} frames of the same workload in {b['seconds']:.1f} s ({b['mode']}: median of {m['sequential']['reps']} repetitions, "
+            f"min {b['spread'][0]:.1f} / max {b['spread'][1]:.1f} frames/s); sequential (how the reference's ./run executes, OpenCV "
+            f"x{m['sequential']['opencv_threads']} threads): {m['sequential']['median']:.1f} frames/s; process pool: "
+            f"{m['pool'].get('median', float('nan')):.1f} frames/s on {m['pool'].get('busy_workers', 0)} single-thread workers "
+            f"(scaling curve {m['pool'].get('scaling_curve_fps')}); cv2 {m['cv2']} (the OpenCV build the reference's calls resolve to) "
+            f"through the oracle/ref_path.py glue restatement; affinity cores={m['affinity_cores']}")
 
 
 def sequence_mode(ctx, torch, cal, n_frames):
@@ -295,33 +358,26 @@ def sequence_mode(ctx, torch, cal, n_frames):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own OpenCV CPU implementation on the host cores."""
+    """--impl reference: the reference's own OpenCV CPU implementation on the host cores (rank 0 only)."""
     if rank != 0:
         return
     from visual_odom_b200 import synth
     global W_IMG, H_IMG
     W_IMG, H_IMG = args.width, args.height
-    from visual_odom_b200 import synth as _s
-    cal = _s.KITTI00 if args.calib == "kitti" else _s.ZED
+    cal = synth.KITTI00 if args.calib == "kitti" else synth.ZED
     units = [synth.stereo_unit(W_IMG, H_IMG, s, cal=cal) for s in range(args.units)]
-    # each step = a bounded sample of the workload (args.units frames per process group) on the CPU
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_frames(units, args.features, len(units))
-    frames_total = max(len(units), min(args.steps * len(units), 600))
-    best = cpu_reference_best(units, args, frames_total)
-    cores = best["cores"]
-    t_total = args.steps * len(units) / best["value"]
-    value = args.steps * len(units) / t_total
+    m = cpu_reference_measure(units, args, seconds_per_mode=args.cpu_seconds, reps=3)
+    value = m["best"]["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.units / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/i32 fixed point + f32 (LK), f64 (pose)", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{best['frames']} frames of the workload in {best['seconds']:.1f} s; {best['how']}; cv2 "
-                                   f"{__import__('cv2').__version__} (the OpenCV build the reference's calls resolve to) through the "
-                                   f"oracle/ref_path.py glue restatement; affinity cores={best['affinity_cores']}; tried: {best['tried']}"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": m["best"]["cores"], "kind": "port", "sample": cpu_sample_text(m),
+                         "sequential": m["sequential"], "pool": m["pool"],
+                         "timing": f"time-based: >= {args.cpu_seconds:.0f} s of timed work per mode in 3 repetitions, median reported "
+                                   f"(--steps / --warmup do not shorten it); one step = {args.units} frames"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -334,6 +390,170 @@ def workload_config(args, world):
                         f"{args.units} independent stereo pairs per step per GPU",
             "units_per_gpu": args.units, "global_units": args.units * world, "features": args.features,
             "l2": "flushed before every step's submission by a 256 MiB write (inside the timed region)", "parallelism": f"units sharded over {world} GPU(s), no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_unit_outputs(u, n_feat, t_prev=(0.0, 0.0, -0.8)):
+    """Everything the reference hands back for one work unit, from cv2 through the verbatim glue (the parity oracle)."""
+    from oracle import ref_path
+    from visual_odom_b200 import synth
+    corners = ref_path.fast_cv2(u["l0"])
+    pts = synth.select_features(corners, n_feat)
+    fs = ref_path.FeatureSet(); fs.points = pts; fs.ages = np.zeros(len(pts), np.int32)
+    cm = ref_path.circular_matching(u["l0"], u["r0"], u["l1"], u["r1"], pts, fs, "cv2")
+    ok = ref_path.check_valid_match(cm["l0"], cm["l0_ret"], 0)
+    pL0, pR0, pL1, pR1 = (ref_path.remove_invalid_points(cm[k], ok) for k in ("l0", "r0", "l1", "r1"))
+    X = ref_path.triangulate(u["P_l"], u["P_r"], pL0, pR0, "cv2")
+    R, t, inl, rvec = ref_path.tracking_frame2frame(u["P_l"], pL0, pL1, X, np.array(t_prev, np.float64), "cv2")
+    return dict(kept_idx=cm["kept_idx"][ok], l0=pL0, r0=pR0, l1=pL1, r1=pR1, X=X, inliers=np.asarray(inl).ravel(), R=R, t=np.asarray(t).ravel())
+
+
+def check_against_oracle(got, res, ref):
+    """north_star gates: tracked-feature indices and RANSAC inlier list bit-exact, positions / [R|t] within 1e-4 relative
+    (the positions are in fact compared bit for bit)."""
+    bad = []
+    if not np.array_equal(got["kept_idx"], ref["kept_idx"]):
+        bad.append("kept_idx")
+    for k in ("l0", "r0", "l1", "r1"):
+        if got[k].shape != ref[k].shape or not np.array_equal(got[k], ref[k]):
+            bad.append(k)
+    if got["X"].shape != ref["X"].shape or not np.array_equal(got["X"], ref["X"]):
+        bad.append("X")
+    if not np.array_equal(got["inliers"], ref["inliers"]):
+        bad.append("inliers")
+    if np.linalg.norm(res["R"] - ref["R"]) > 1e-4 * np.linalg.norm(ref["R"]):
+        bad.append("R")
+    if np.linalg.norm(res["tvec"] - ref["t"]) > 1e-4 * max(np.linalg.norm(ref["t"]), 1e-12):
+        bad.append("t")
+    return bad
+
+
+class Point:
+    """One workload point (image size, features, units per step) measured on a context: the pipelined resident pass
+    (`value`), the LK kernel alone on one stream (roofline) and the pipelined end-to-end pass with pinned host images in
+    and the full per-unit outputs back (`e2e`)."""
+
+    def __init__(self, ctx, torch, stream, flush, pinned, feats, B, w, h, P_l, P_r, barrier, world, gather=None, my_units=None):
+        self.ctx, self.torch, self.stream, self.flush, self.B, self.feats = ctx, torch, stream, flush, B, feats
+        self.w, self.h, self.barrier, self.world, self.gather, self.my_units = w, h, barrier, world, gather, my_units
+        ctx.batch_configure(w, h, 2 * B, P_l, P_r)                  # two slot ranges of B (two submissions in flight)
+        spec = [dict(p, n_select=feats, t_prev=(0.0, 0.0, -0.8)) for p in pinned]
+        self.arr, self.keep, self.pitch = ctx.make_units(spec)
+        self.arr2, self.keep2, _ = ctx.make_units(spec + spec)
+        self.into = [[dict(pts4=np.zeros((4, feats, 2), np.float32), kept_idx=np.zeros(feats, np.int32),
+                           X=np.zeros((feats, 3), np.float32), inliers=np.zeros(feats, np.int32)) for _ in range(B)] for _ in range(2)]
+        self.last_outputs = None
+        self.d2h_outputs = 0
+
+    def _timed(self, fn, steps):
+        torch = self.torch
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.barrier()
+        t0 = time.perf_counter()
+        out = fn(steps, ev)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        return ev[0].elapsed_time(ev[1]), wall, out
+
+    # ---- resident inputs: both ranges uploaded once, a step re-runs one range (units = NULL) -----------------
+    def resident_steps(self, n, ev=None):
+        ctx, B, flush = self.ctx, self.B, self.flush
+        out = None
+        if ev:
+            ev[0].record(self.stream)
+        flush.fill_(1)
+        ctx.batch_submit(None, 0, self.pitch, n_units=B)
+        for s in range(n):
+            if s + 1 < n:
+                flush.fill_(s & 0xFF)
+                ctx.batch_submit(None, ((s + 1) & 1) * B, self.pitch, n_units=B)
+            out = ctx.batch_wait((s & 1) * B, B)
+        if ev:
+            ev[1].record(self.stream)
+        return out
+
+    def measure_resident(self, steps, warmup, blocks=1):
+        self.ctx.set_option("batch_outputs", 0)
+        self.ctx.batch_upload(self.arr2, self.pitch)
+        self.resident_steps(max(2, warmup))
+        self.torch.cuda.synchronize()
+        l0 = self.ctx.kernel_launches()
+        ms, res = [], None
+        for _ in range(blocks):
+            t, _w, res = self._timed(self.resident_steps, steps)
+            ms.append(t)
+        launches = (self.ctx.kernel_launches() - l0) // blocks
+        return ms, res, launches
+
+    # ---- the LK kernel alone: one stream, plain launches, bracketed by its own CUDA events --------------------
+    def measure_lk_alone(self, steps, warmup):
+        ctx, torch = self.ctx, self.torch
+        ctx.batch_upload(self.arr, self.pitch)
+        ctx.set_option("batch_streams", 1)
+        ctx.set_option("graphs", 0)
+        for _ in range(max(3, warmup)):
+            ctx.batch_run()
+        torch.cuda.synchronize()
+        ctx.lk_kernel_time(reset=True)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s in range(steps):
+            self.flush.fill_(s & 0xFF)
+            evs[s][0].record(self.stream)
+            ctx.batch_run()
+            evs[s][1].record(self.stream)
+        torch.cuda.synchronize()
+        t_single = sum(a.elapsed_time(b) for a, b in evs)
+        lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
+        res = ctx.batch_download(self.B)
+        ctx.set_option("batch_streams", 2)
+        ctx.set_option("graphs", 1)
+        return lk_ms / max(lk_n, 1), lk_ms, t_single, sum(r["n_features"] for r in res)
+
+    # ---- end to end: pinned host images in, records + all point lists out, every step -------------------------
+    def e2e_steps(self, n, ev=None):
+        ctx, B = self.ctx, self.B
+        out = None
+        if ev:
+            ev[0].record(self.stream)
+        ctx.batch_submit(self.arr, 0, self.pitch)
+        for s in range(n):
+            if s + 1 < n:
+                ctx.batch_submit(self.arr, ((s + 1) & 1) * B, self.pitch)
+            slot = (s & 1) * B
+            out = ctx.batch_wait(slot, B)
+            if self.full_outputs:                              # what matchingFeatures / trackingFrame2Frame hand back
+                self.last_outputs = [ctx.batch_outputs(slot + u, out[u], into=self.into[s & 1][u]) for u in range(B)]
+            if self.gather is not None:                        # result gather: fixed-size records over NCCL, non-blocking
+                from visual_odom_b200 import dist as vd
+                self.gather.post([vd.result_to_record(r) for r in out], self.my_units)
+        if self.gather is not None:
+            self.tables = self.gather.drain()                  # the last tables arrive inside the timed region
+        if ev:
+            ev[1].record(self.stream)
+        return out
+
+    def measure_e2e(self, steps, warmup, full_outputs=True, blocks=1):
+        self.full_outputs = full_outputs
+        self.ctx.set_option("batch_outputs", 1 if full_outputs else 0)
+        self.e2e_steps(max(2, warmup))
+        self.torch.cuda.synchronize()
+        ms, walls, res = [], [], None
+        for _ in range(blocks):
+            t, w, res = self._timed(self.e2e_steps, steps)
+            ms.append(t); walls.append(w)
+        if full_outputs and self.last_outputs:
+            self.d2h_outputs = self.B * self.last_outputs[0]["d2h_bytes"]
+        return ms, walls, res
+
+
+def lk_profile_constants():
+    """ncu-derived constants of the LK kernel (committed under profiles/, refreshed per round): DRAM traffic per launch,
+    issue-slot utilisation and warp instructions per feature-ring."""
+    tp = os.path.join(ROOT, "profiles", "lk_traffic.json")
+    try:
+        return json.load(open(tp))
+    except Exception:
+        return {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -369,28 +589,26 @@ def main():
     cal = synth.KITTI00 if args.calib == "kitti" else synth.ZED
     units = [synth.stereo_unit(W_IMG, H_IMG, s, cal=cal) for s in seeds]
 
-    # pinned host copies of the images (what a capture / decode thread would hand over)
-    pinned = []
-    for u in units:
-        d = {}
-        for k in ("l0", "r0", "l1", "r1"):
-            t = torch.empty((H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
-            t.numpy()[:] = u[k]
-            d[k] = t.numpy()
-        pinned.append(d)
-    keep_alive = pinned
+    def pin_units(us, w, h):
+        out = []
+        for u in us:                    # pinned host copies of the images (what a capture / decode thread would hand over)
+            d = {}
+            for k in ("l0", "r0", "l1", "r1"):
+                t = torch.empty((h, w), dtype=torch.uint8, pin_memory=True)
+                t.numpy()[:] = u[k]
+                d[k] = t.numpy()
+            d["_keep"] = None
+            out.append(d)
+        return out
 
+    pinned = pin_units(units, W_IMG, H_IMG)
     ctx = Context(local_rank, max_features=max(2048, args.features), max_units=2 * B)
-    # a real (non-default) stream shared by torch's events and the library's kernels
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    for opt in ("graphs", "priorities", "batch_graphs"):   # A/B switches for experiments, e.g. VO_OPT_PRIORITIES=0 VO_OPT_BATCH_GRAPHS=1
+    for opt in ("graphs", "priorities", "batch_graphs", "lk_span", "lk_ctas_per_sm", "lk_kernel"):   # A/B switches, e.g. VO_OPT_LK_SPAN=16
         if os.environ.get("VO_OPT_" + opt.upper()) is not None:
             ctx.set_option(opt, float(os.environ["VO_OPT_" + opt.upper()]))
-    ctx.batch_configure(W_IMG, H_IMG, 2 * B, units[0]["P_l"], units[0]["P_r"])     # two slot ranges of B (pipelined e2e)
-    arr, keep, pitch = ctx.make_units([dict(p, n_select=args.features, t_prev=(0.0, 0.0, -0.8)) for p in pinned])
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -398,160 +616,130 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- resident-input throughput (`value`) ----------------
-    # Both slot ranges (2 x B units) are uploaded once; a step re-runs one resident range of B units
-    # (vo_batch_submit with units = NULL) and reads its B result records back.  Two steps are in flight, as in `e2e`;
-    # the L2 is flushed by a 256 MiB write before every submission (on the caller's stream, so the submission waits
-    # for it; the flush is INSIDE the timed region).
-    arr2, keep2, _ = ctx.make_units([dict(p, n_select=args.features, t_prev=(0.0, 0.0, -0.8)) for p in pinned + pinned])
-    ctx.batch_upload(arr2, pitch)
-
-    def resident_steps(n, ev_pair=None):
-        out = None
-        if ev_pair:
-            ev_pair[0].record(stream)
-        flush.fill_(1)
-        ctx.batch_submit(None, 0, pitch, n_units=B)
-        for s in range(n):
-            if s + 1 < n:
-                flush.fill_(s & 0xFF)
-                ctx.batch_submit(None, ((s + 1) & 1) * B, pitch, n_units=B)
-            out = ctx.batch_wait((s & 1) * B, B)
-        if ev_pair:
-            ev_pair[1].record(stream)
-        return out
-
-    resident_steps(max(2, args.warmup))
-    torch.cuda.synchronize()
-    ctx.lk_kernel_time(reset=True)
-    launches0 = ctx.kernel_launches()
-    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    gather = vd.AsyncRecordGather(world * B, device="cuda") if world > 1 else None
+    P = units[0]
+    pt = Point(ctx, torch, stream, flush, pinned, args.features, B, W_IMG, H_IMG, P["P_l"], P["P_r"], barrier, world, gather, my_units)
+    BLOCKS = 5                            # the K-step timed region is repeated and the median block reported (a block is ~40 ms)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    res = resident_steps(args.steps, ev)
-    barrier()
-    t_dev_ms = ev[0].elapsed_time(ev[1])
-    launches = ctx.kernel_launches() - launches0
-    feats_per_launch = sum(r["n_features"] for r in res)
-
-    ctx.batch_upload(arr, pitch)          # back to one resident range of B units for the single-stream pass
-    # ---------------- LK kernel alone (roofline): one stream, so its CUDA-event time is not shared ----------------
-    ctx.set_option("batch_streams", 1)
-    ctx.set_option("graphs", 0)          # plain launches: the LK kernel is bracketed by its own CUDA events
-    for _ in range(args.warmup):
-        ctx.batch_run()
-    torch.cuda.synchronize()
-    ctx.lk_kernel_time(reset=True)
-    ev1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s in range(args.steps):
-        flush.fill_(s & 0xFF)
-        ev1[s][0].record(stream)
-        ctx.batch_run()
-        ev1[s][1].record(stream)
-    torch.cuda.synchronize()
-    t_single_ms = sum(a.elapsed_time(b) for a, b in ev1)
-    lk_ms, lk_n = ctx.lk_kernel_time(reset=True)
-    ctx.set_option("batch_streams", 2)
-    ctx.set_option("graphs", 1)
-
-    # ---------------- end-to-end through the C-ABI with host buffers (`e2e`) ----------------
-    # Pipelined submissions (vo_batch_submit / vo_batch_wait): every step uploads its B stereo pair-of-pairs from pinned
-    # host memory into one of two resident slot ranges, runs the whole path and reads its B result records back; step
-    # s+1 is submitted before step s is waited for, so the copy and the latency-bound PnP tail of one step run under
-    # the LK ring of the other.  Every step's H2D, kernels and D2H are inside the timed region.
-    def e2e_steps(n, ev_pair=None):
-        out = None
-        if ev_pair:
-            ev_pair[0].record(stream)
-        ctx.batch_submit(arr, 0, pitch)
-        for s in range(n):
-            if s + 1 < n:
-                ctx.batch_submit(arr, ((s + 1) & 1) * B, pitch)
-            out = ctx.batch_wait((s & 1) * B, B)
-            if world > 1:                                    # result gather: fixed-size records over NCCL
-                vd.gather_records([vd.result_to_record(r) for r in out], my_units, world * B, device="cuda")
-        if ev_pair:
-            ev_pair[1].record(stream)
-        return out
-
-    e2e_steps(max(2, args.warmup))
-    torch.cuda.synchronize()
-    barrier()
-    e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    t_wall0 = time.perf_counter()
-    res_e2e = e2e_steps(args.steps, e2e_ev)
-    barrier()
-    t_e2e_wall = time.perf_counter() - t_wall0
-    t_e2e_ms = e2e_ev[0].elapsed_time(e2e_ev[1])
+    ms_res, res, launches = pt.measure_resident(args.steps, args.warmup, BLOCKS)
+    lk_avg_ms, lk_ms, t_single_ms, feats_per_launch = pt.measure_lk_alone(args.steps, args.warmup)
+    ms_e2e, wall_e2e, res_e2e = pt.measure_e2e(args.steps, args.warmup, True, BLOCKS)
     clocks = sampler.stop() if sampler else None
+    ms_sum, _w, res_sum = pt.measure_e2e(args.steps, args.warmup, False, 1)       # records only (round-1 definition of e2e)
 
-    # max over ranks (device-timed)
-    tt = torch.tensor([t_dev_ms, t_e2e_ms, lk_ms, float(feats_per_launch)], dtype=torch.float64, device="cuda")
+    # ---- parity on hardware: one unit of THIS rank against cv2 through the reference glue (outside the timed region) ----
+    t_or = time.perf_counter()
+    last_slot_unit = 0                                         # unit 0 of the rank's range, outputs of the last e2e step
+    ref = reference_unit_outputs(units[last_slot_unit], args.features)
+    bad = check_against_oracle(pt.last_outputs[last_slot_unit], res_e2e[last_slot_unit], ref)
+    oracle_s = time.perf_counter() - t_or
+    ok_t = torch.tensor([0.0 if bad else 1.0], dtype=torch.float64, device="cuda")
+
+    # max over ranks (device-timed), block by block
+    tt = torch.tensor(ms_res + ms_e2e + ms_sum + [lk_ms, float(feats_per_launch)], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    else:
-        tmax = tt; tsum = tt
-    t_dev_ms, t_e2e_ms = float(tmax[0]), float(tmax[1])
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    tt = tt.cpu().numpy()
+    ms_res, ms_e2e, ms_sum = list(tt[:BLOCKS]), list(tt[BLOCKS:2 * BLOCKS]), float(tt[2 * BLOCKS])
+    parity_ok = bool(ok_t.item() >= 1.0)
+    t_dev_ms, t_e2e_ms = _median(ms_res), _median(ms_e2e)
 
     if rank == 0:
         frames = world * B * args.steps
         value = frames / (t_dev_ms * 1e-3)
         e2e_value = frames / (t_e2e_ms * 1e-3)
         peak, peak_src = peaks()
-        lk_avg_ms = lk_ms / max(lk_n, 1)
-        alg_bytes = LK_BYTES_PER_FEATURE * feats_per_launch
-        achieved = alg_bytes / (lk_avg_ms * 1e-3) / 1e9 if lk_avg_ms > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "lk_traffic.json")
-        if os.path.exists(tp):
+        prof = lk_profile_constants()
+
+        def roofline_of(lk_avg, nfeat):
+            alg = LK_BYTES_PER_FEATURE * nfeat
+            ach = alg / (lk_avg * 1e-3) / 1e9 if lk_avg > 0 else 0.0
+            return alg, ach
+
+        alg_bytes, achieved = roofline_of(lk_avg_ms, feats_per_launch)
+        # ---- the other BASELINE.json configs on the same box, N = 1: feature sweep, 1080p / 4000, a single pair, a sequence ----
+        sweep, single_pair, seq = [], None, None
+        if world == 1 and args.sweep:
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        if world == 1:
-            cpu_best = cpu_reference_best(units, args, args.cpu_sample)
-        else:                                    # the host baseline is an N = 1 measurement (see --impl reference)
-            cpu_best = {"value": None, "seconds": 0.0, "cores": 0, "frames": 0, "how": "not measured at N > 1", "tried": [],
-                        "affinity_cores": len(os.sched_getaffinity(0))}
-        cpu_fps, cpu_dt, cores = cpu_best["value"], cpu_best["seconds"], cpu_best["cores"]
-        seq = None
-        if world == 1 and args.sequence > 0:
-            try:
-                seq = sequence_mode(ctx, torch, cal, args.sequence)
+                ctx.close()
+                ctx = Context(local_rank, max_features=8192, max_units=2 * B)
+                ctx.set_stream(stream.cuda_stream)
+
+                def run_point(us_pinned, feats, b, w, h, Pm, steps=5):
+                    q = Point(ctx, torch, stream, flush, us_pinned[:b], feats, b, w, h, Pm["P_l"], Pm["P_r"], barrier, 1)
+                    r_ms, r_res, _l = q.measure_resident(steps, 3, 3)
+                    lk_a, _lm, t_s, nf = q.measure_lk_alone(steps, 3)
+                    e_ms, _ww, _er = q.measure_e2e(steps, 3, True, 3)
+                    alg, ach = roofline_of(lk_a, nf)
+                    return {"width": w, "height": h, "features": feats, "units_per_step": b, "steps": steps,
+                            "value_fps": b * steps / (_median(r_ms) * 1e-3), "e2e_fps": b * steps / (_median(e_ms) * 1e-3),
+                            "lk_avg_launch_ms": lk_a, "lk_algorithmic_GBps": ach, "lk_frac": ach / peak,
+                            "lk_us_per_feature_ring": 1e3 * lk_a / max(nf, 1), "n_valid": [r["n_valid"] for r in r_res][:4]}
+
+                for nf in (500, 1000, 2000, 4000, 8000):        # BASELINE.json configs[4]
+                    sweep.append(run_point(pinned, nf, B, W_IMG, H_IMG, P))
+                single_pair = run_point(pinned, args.features, 1, W_IMG, H_IMG, P, steps=20)     # configs[1]: one pair per step
+                zu = [synth.stereo_unit(1920, 1080, 50 + i, cal=synth.ZED) for i in range(4)]     # configs[2]
+                sweep.append(dict(run_point(pin_units(zu, 1920, 1080), 4000, 4, 1920, 1080, zu[0]), calib="zed"))
+                if args.sequence > 0:
+                    W0, H0 = W_IMG, H_IMG
+                    seq = sequence_mode(ctx, torch, cal, args.sequence)
             except Exception as e:           # a side measurement must never cost the headline line
-                seq = {"error": str(e)[:200]}
+                sweep.append({"error": str(e)[:300]})
+        if world == 1:
+            m = cpu_reference_measure(units, args, seconds_per_mode=args.cpu_seconds, reps=3)
+            cpu = {"value": m["best"]["value"], "unit": "frames/s", "cores": m["best"]["cores"], "kind": "port",
+                   "sample": cpu_sample_text(m), "sequential": m["sequential"], "pool": m["pool"]}
+        else:                                    # the host baseline is an N = 1 measurement (see --impl reference)
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "not measured at N > 1 (rank 0 at N = 1 only)"}
+        d2h_records = B * 152
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/i32 fixed point + f32 (LK), f64 (pose)", "data": "synthetic",
             "config": workload_config(args, world),
+            "timed_blocks_ms": {"resident": [round(x, 3) for x in ms_res], "e2e": [round(x, 3) for x in ms_e2e],
+                                "note": f"the {args.steps}-step timed region is run {BLOCKS} times (barrier + synchronize on both sides "
+                                        "of every block, max over ranks per block); value / e2e use the median block"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * 4 * W_IMG * H_IMG + B * 32,
-                    "d2h_bytes_per_step": B * 152, "ms_per_step": t_e2e_ms / args.steps,
-                    "wall_ms_per_step": 1e3 * t_e2e_wall / args.steps,
-                    "mode": "vo_batch_submit / vo_batch_wait, two submissions of units_per_gpu in flight; timed from the "
-                            "first submit to the last wait, every step's H2D + kernels + D2H inside",
+                    "d2h_bytes_per_step": d2h_records + pt.d2h_outputs, "ms_per_step": t_e2e_ms / args.steps,
+                    "wall_ms_per_step": 1e3 * _median(wall_e2e) / args.steps,
+                    "mode": "vo_batch_submit / vo_batch_wait / vo_batch_outputs, two submissions of units_per_gpu in flight; every step's H2D "
+                            "(4 images per unit from pinned host memory), kernels, and D2H of the result records AND of every unit's point "
+                            "lists (4 x n_valid points, tracked-feature indices, points3D, inlier list: one packed copy per submission) "
+                            "are inside the timed region" + ("; the NCCL all-gather of the records runs non-blocking on a side stream and "
+                                                             "is drained inside the timed region" if world > 1 else ""),
+                    "summary_only": {"value": frames / (ms_sum * 1e-3), "d2h_bytes_per_step": d2h_records,
+                                     "note": "round-1 definition: result records only"},
                     "equals_resident_results": all(a["n_inliers"] == b["n_inliers"] and np.array_equal(a["tvec"], b["tvec"])
-                                                   for a, b in zip(res_e2e, res))},
+                                                   for a, b in zip(res_e2e, res)),
+                    "single_pair": single_pair, "sequence": seq},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_lk_ring", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "features_per_launch": feats_per_launch,
                          "avg_launch_ms": lk_avg_ms, "lk_share_of_step": lk_ms / t_single_ms if t_single_ms else None,
                          "single_stream_ms_per_step": t_single_ms / args.steps,
-                         "note": "algorithmic bytes per SURVEY.md 8(d); the kernel is ALU/latency bound, see DESIGN.md"},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_best['frames']} frames of the same workload in {cpu_dt:.1f} s; {cpu_best['how']}; cv2 (the "
-                                       f"OpenCV the reference's calls resolve to) through oracle/ref_path.py glue; affinity cores="
-                                       f"{cpu_best['affinity_cores']}; tried: {cpu_best['tried']}"},
+                         "issue_frac": prof.get("issue_active_frac"),
+                         "warp_inst_per_feature_ring": prof.get("warp_inst_per_feature_ring"),
+                         "profile_source": prof.get("source"),
+                         "sweep": sweep,
+                         "note": "algorithmic bytes per SURVEY.md 8(d); the kernel is issue bound (pyramids are L2 resident), see DESIGN.md; "
+                                 "issue_frac / warp_inst_per_feature_ring come from the committed ncu capture named in profile_source"},
+            "cpu_baseline": cpu,
             "clocks": clocks,
-            "sequence_mode": seq,
-            "parity": {"n_valid": [r["n_valid"] for r in res], "n_inliers": [r["n_inliers"] for r in res]},
+            "parity": {"vs_oracle": parity_ok, "units_checked": world, "mismatches_rank0": bad,
+                       "oracle": "cv2 4.13.0 through oracle/ref_path.py (the reference's glue), one unit per rank, outside the timed region",
+                       "oracle_seconds_rank0": oracle_s,
+                       "n_valid": [r["n_valid"] for r in res], "n_inliers": [r["n_inliers"] for r in res]},
         }
         print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

@@ -9,6 +9,7 @@ Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys
+import zlib
 
 import numpy as np
 
@@ -23,6 +24,10 @@ CONFIGS = {
     "kitti_1241x376_n2000_s0": (1241, 376, 0, "v1", 2000, "kitti"),
     "kitti_1241x376_n500_s7_v0": (1241, 376, 7, "v0", 500, "kitti"),
     "small_640x240_n300_s11": (640, 240, 11, "v1", 300, "kitti"),
+    # BASELINE.json configs[4]: the feature-count sweep points that had no oracle comparison (500 and 2000 are above)
+    "kitti_1241x376_n1000_s1": (1241, 376, 1, "v1", 1000, "kitti"),
+    "kitti_1241x376_n4000_s2": (1241, 376, 2, "v1", 4000, "kitti"),
+    "kitti_1241x376_n8000_s3": (1241, 376, 3, "v1", 8000, "kitti"),
 }
 T_PREV = np.array([0.0, 0.0, -0.8])
 
@@ -38,8 +43,11 @@ def reference_outputs(w, h, seed, scene, n_sel, cal):
     pL0, pR0, pL1, pR1 = (ref_path.remove_invalid_points(cm[k], ok) for k in ("l0", "r0", "l1", "r1"))
     X = ref_path.triangulate(u["P_l"], u["P_r"], pL0, pR0, "cv2")
     R, t, inl, rvec = ref_path.tracking_frame2frame(u["P_l"], pL0, pL1, X, T_PREV, "cv2")
-    return dict(n_corners=np.int32(len(corners)), corners_head=corners[:64], pts=pts,
-                raw_r0=cm["raw"]["r0"], raw_r1=cm["raw"]["r1"], raw_l1=cm["raw"]["l1"], raw_l0_ret=cm["raw"]["l0_ret"],
+    # the per-call raw outputs are stored up to 2000 features; above that a position checksum per call keeps the fixture
+    # small (the kept point lists below are subsets of the raw outputs and stay complete)
+    raw = {("raw_" + k): cm["raw"][k] for k in ("r0", "r1", "l1", "l0_ret")} if n_sel <= 2000 else {}
+    raw_crc = np.array([zlib.crc32(np.ascontiguousarray(cm["raw"][k]).tobytes()) for k in ("r0", "r1", "l1", "l0_ret")], np.uint32)
+    return dict(n_corners=np.int32(len(corners)), corners_head=corners[:64], pts=pts, raw_crc=raw_crc, **raw,
                 status=cm["raw"]["status"], kept3=cm["kept_idx"], kept=cm["kept_idx"][ok],
                 l0=pL0, r0=pR0, l1=pL1, r1=pR1, X=X, inliers=inl, R=R, t=t, rvec=rvec,
                 image_crc=np.array([int(np.bitwise_xor.reduce(u[k].astype(np.uint32).ravel() * np.arange(1, w * h + 1, dtype=np.uint32)))
@@ -49,7 +57,10 @@ def reference_outputs(w, h, seed, scene, n_sel, cal):
 
 if __name__ == "__main__":
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         o = reference_outputs(*cfg)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **o)
         print(name, "corners", int(o["n_corners"]), "tracked", len(o["kept3"]), "valid", len(o["kept"]), "inliers", len(o["inliers"]))

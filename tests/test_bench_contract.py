@@ -13,7 +13,7 @@ pytest.importorskip("cv2")
 
 def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                        "--warmup", "0", "--units", "2", "--features", "300", "--width", "640", "--height", "240"],
+                        "--warmup", "0", "--units", "2", "--features", "300", "--width", "640", "--height", "240", "--cpu-seconds", "2"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -28,6 +28,11 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames" in cb["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both ways of running the CPU path are always reported, each as median / min / max of 3 repetitions
+    seq, pool = cb["sequential"], cb["pool"]
+    assert seq["reps"] == 3 and seq["min"] <= seq["median"] <= seq["max"] and seq["seconds"] >= 1.9
+    assert "error" in pool or (pool["reps"] == 3 and pool["min"] <= pool["median"] <= pool["max"] and pool["busy_workers"] >= 1)
+    assert cb["value"] == max(seq["median"], pool.get("median", 0.0))
 
 
 def test_non_rank0_reference_arm_exits_quietly():

@@ -37,6 +37,12 @@ def _worker(rank, world, port, n_units, out_path):
     mine = vd.unit_assignment(n_units, world)[rank]
     recs = [vd.result_to_record(_process_unit(table[u])) for u in mine]
     full = vd.gather_records(recs, mine, n_units)
+    # the non-blocking gather of a pipelined loop: three posts (more than... fewer than the ring depth), then a ring wrap
+    ag = vd.AsyncRecordGather(n_units, device="cpu", depth=2)
+    for k in range(3):
+        ag.post([r + k for r in recs], mine)
+    tabs = ag.drain()
+    assert len(tabs) == 3 and all(np.array_equal(t, full + k) for k, t in enumerate(tabs))
     if rank == 0:
         np.save(out_path, full)
     dist.destroy_process_group()

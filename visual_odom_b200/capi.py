@@ -99,6 +99,7 @@ SIGNATURES = {
     "vo_pose_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vo_seq_pose": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vo_batch_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
 }
 
 _lib = None
@@ -340,6 +341,20 @@ class Context:
         self._check(self.lib.vo_batch_fetch(self.h, unit, _p(pts_in), _p(pts4), _p(kept), _p(X), _p(inl)))
         return dict(pts_in=pts_in[:nf], l0=pts4[0, :nv], r0=pts4[1, :nv], l1=pts4[2, :nv], r1=pts4[3, :nv],
                     kept_idx=kept[:nv], X=X[:nv], inliers=inl[:ni])
+
+    def batch_outputs(self, unit, res, into=None):
+        """Point lists of a waited submission from the pinned block its single D2H filled (set_option("batch_outputs", 1)).
+        `into` = preallocated dict(pts4, kept_idx, X, inliers) to avoid allocations in a timed loop."""
+        nv, ni = res["n_valid"], res["n_inliers"]
+        if into is None:
+            into = dict(pts4=np.zeros((4, max(nv, 1), 2), np.float32), kept_idx=np.zeros(max(nv, 1), np.int32),
+                        X=np.zeros((max(nv, 1), 3), np.float32), inliers=np.zeros(max(ni, 1), np.int32))
+        nb = C.c_size_t(0)
+        self._check(self.lib.vo_batch_outputs(self.h, unit, _p(into["pts4"]), _p(into["kept_idx"]), _p(into["X"]), _p(into["inliers"]),
+                                              C.byref(nb)))
+        flat = into["pts4"].reshape(-1, 2)            # the C side packs the four lists back to back (n_valid each)
+        return dict(l0=flat[0:nv], r0=flat[nv:2 * nv], l1=flat[2 * nv:3 * nv], r1=flat[3 * nv:4 * nv], kept_idx=into["kept_idx"][:nv],
+                    X=into["X"][:nv], inliers=into["inliers"][:ni], d2h_bytes=int(nb.value))
 
     # ---- streaming sequence mode -------------------------------------------------------------------
     def seq_begin(self, left0, right0, P_l, P_r):

@@ -19,6 +19,53 @@ __global__ void k_pack_counts(vo_unit_result_dev* res, const int* n_pts, const i
     res[u].n_valid = n5[u];
 }
 
+// Packed outputs of one unit: float2 pts4[4][per] (L0, R0, L1, R1 of the valid tracks) | int kept_idx[per] |
+// float3 X[per] | int inliers[per], `per` point slots each (only the first n_valid / n_inliers are written).
+#define VO_OUT_BYTES_PER_SLOT (4 * sizeof(float2) + sizeof(int) + sizeof(float3) + sizeof(int))
+__global__ void k_pack_outputs(uint8_t* __restrict__ out, size_t stride, int per, const float2* __restrict__ valid4, size_t cs,
+                               const int* __restrict__ idx5, const float3* __restrict__ X, const int* __restrict__ inliers,
+                               const int* __restrict__ n5, const vo_unit_result_dev* __restrict__ res, int cap)
+{
+    const int u = blockIdx.x;
+    const int nv = min(n5[u], per), ni = min(res[u].n_inliers, per);
+    float2* o4 = reinterpret_cast<float2*>(out + (size_t)u * stride);
+    int* ok = reinterpret_cast<int*>(o4 + 4 * (size_t)per);
+    float* oX = reinterpret_cast<float*>(ok + per);
+    int* oi = reinterpret_cast<int*>(oX + 3 * (size_t)per);
+    const size_t ub = (size_t)u * cap;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) o4[(size_t)k * per + i] = valid4[k * cs + ub + i];
+        ok[i] = idx5[ub + i];
+        const float3 x = X[ub + i];
+        oX[3 * i] = x.x; oX[3 * i + 1] = x.y; oX[3 * i + 2] = x.z;
+    }
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) oi[i] = inliers[ub + i];
+}
+
+// device + pinned blocks of the packed outputs, sized for the configured batch and the resident feature counts
+static int ensure_outputs(vo_ctx* ctx)
+{
+    int per = ctx->batch_max_pts > 0 ? ctx->batch_max_pts : ctx->cap;
+    per = (per + 63) / 64 * 64;
+    if (per > ctx->cap) per = ctx->cap;
+    const size_t stride = ((size_t)per * VO_OUT_BYTES_PER_SLOT + 255) / 256 * 256;
+    if (ctx->d_out && ctx->out_per == per && ctx->h_out && ctx->out_units >= ctx->units) return VO_OK;
+    int rc = vo_drain_pending(ctx);
+    if (rc) return rc;
+    if (!ctx->d_out || ctx->out_per != per) {
+        void* q = nullptr;                      // freed with the batch state (ctx->allocs)
+        VO_CUDA_CHECK(cudaMalloc(&q, stride * ctx->units + 256));
+        ctx->allocs.push_back(q);
+        ctx->d_out = (uint8_t*)q;
+        vo_drop_graphs(ctx);                    // graphs hold the old pointer / stride
+    }
+    if (ctx->h_out) { cudaFreeHost(ctx->h_out); ctx->h_out = nullptr; }
+    VO_CUDA_CHECK(cudaMallocHost(&ctx->h_out, stride * ctx->units + 256));
+    ctx->out_units = ctx->units; ctx->out_per = per; ctx->out_stride = stride;
+    return VO_OK;
+}
+
 extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const float P_l[12], const float P_r[12])
 {
     if (!ctx) return VO_E_INVALID;
@@ -26,9 +73,7 @@ extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const 
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     int rc = vo_ensure_state(ctx, w, h, n_units, 4);
     if (rc) return rc;
-    memcpy(ctx->P_l, P_l, 12 * sizeof(float));
-    memcpy(ctx->P_r, P_r, 12 * sizeof(float));
-    ctx->have_P = true;
+    vo_set_calibration(ctx, P_l, P_r);
     ctx->batch_units = n_units;
     ctx->batch_uploaded = 0;
     return VO_OK;
@@ -158,7 +203,10 @@ static int run_range_launch(vo_ctx* ctx, const View& v)
         VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ctx->hi_ev[c][1], 0));
     }
     const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};      // ring L0->R0->R1->L1->L0 (planes L0,R0,L1,R1)
-    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
+    ctx->lk_per_unit = ctx->batch_max_pts;                      // no unit of the resident batch has more live features
+    rc = vo_run_lk_ring(ctx, v, 4, ip, in, false);
+    ctx->lk_per_unit = 0;
+    if (rc) return rc;
     if (c >= 0) {
         VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][2], v.s));
         VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ctx->hi_ev[c][2], 0));
@@ -191,7 +239,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
     if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
-        if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma) {
+        if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma && g.s == v.s) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));
             ctx->launches += g.launches;
             return VO_OK;
@@ -207,7 +255,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     VO_CUDA_CHECK(e);
     vo_ctx::RangeGraph g;
-    g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma;
+    g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma; g.s = v.s;
     g.launches = ctx->launches - before;
     VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
@@ -325,6 +373,8 @@ extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit
     }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     if ((rc = ensure_side_streams(ctx))) return rc;
+    if (max_pts > ctx->batch_max_pts || units) ctx->batch_max_pts = max_pts;
+    if (ctx->batch_outputs && (rc = ensure_outputs(ctx))) return rc;
     vo_ctx::Pending* slot = nullptr;
     for (auto& p : ctx->pending) if (!p.active) { slot = &p; break; }
     if (!slot) {
@@ -345,6 +395,16 @@ extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit
     if ((rc = run_range(ctx, View{first_unit, n_units, st}))) return rc;
     vo_unit_result_dev* h_res = pinned_results(ctx);
     VO_CUDA_CHECK(cudaMemcpyAsync(h_res + first_unit, ctx->d_results + first_unit, (size_t)n_units * sizeof(vo_unit_result_dev), cudaMemcpyDeviceToHost, st));
+    if (ctx->batch_outputs) {                    // the point lists of the submission: one packed block, one copy
+        const size_t cs = (size_t)ctx->units * ctx->cap, ub = (size_t)first_unit * ctx->cap;
+        k_pack_outputs<<<n_units, 256, 0, st>>>(ctx->d_out + (size_t)first_unit * ctx->out_stride, ctx->out_stride, ctx->out_per,
+                                               ctx->d_valid4 + ub, cs, ctx->d_idx5 + ub, ctx->d_X + ub, ctx->d_inliers + ub,
+                                               ctx->d_n5 + first_unit, ctx->d_results + first_unit, ctx->cap);
+        ctx->launches += 1;
+        VO_CUDA_CHECK(cudaGetLastError());
+        VO_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out + (size_t)first_unit * ctx->out_stride, ctx->d_out + (size_t)first_unit * ctx->out_stride,
+                                      (size_t)n_units * ctx->out_stride, cudaMemcpyDeviceToHost, st));
+    }
     VO_CUDA_CHECK(cudaEventRecord(slot->done, st));
     slot->u0 = first_unit; slot->n = n_units; slot->active = true;
     return VO_OK;
@@ -364,6 +424,32 @@ extern "C" int vo_batch_wait(vo_ctx* ctx, int first_unit, int n_units, vo_unit_r
         }
     vo_set_error(ctx, "vo_batch_wait: no pending submission for slots [%d, %d)", first_unit, first_unit + n_units);
     return VO_E_INVALID;
+}
+
+// The point lists of a waited submission, from the pinned block its single D2H copy filled ("batch_outputs" = 1):
+// pts4 = [4][n_valid] (L0, R0, L1, R1), kept_idx / X = [n_valid], inliers = [n_inliers]; counts are in the unit's record.
+extern "C" int vo_batch_outputs(vo_ctx* ctx, int unit, vo_point2f* pts4, int32_t* kept_idx, vo_point3f* X, int32_t* inliers,
+                                size_t* d2h_bytes_per_unit)
+{
+    if (!ctx) return VO_E_INVALID;
+    if (!ctx->batch_outputs || !ctx->h_out) { vo_set_error(ctx, "vo_batch_outputs: option batch_outputs is off"); return VO_E_INVALID; }
+    if (unit < 0 || unit >= ctx->batch_uploaded || unit >= ctx->out_units) { vo_set_error(ctx, "unit %d outside the resident batch", unit); return VO_E_INVALID; }
+    for (auto& p : ctx->pending)
+        if (p.active && unit >= p.u0 && unit < p.u0 + p.n) { vo_set_error(ctx, "vo_batch_outputs: unit %d has not been waited for", unit); return VO_E_INVALID; }
+    const vo_unit_result_dev& r = pinned_results(ctx)[unit];
+    const int per = ctx->out_per;
+    const int nv = r.n_valid < per ? r.n_valid : per, ni = r.n_inliers < per ? r.n_inliers : per;
+    const uint8_t* base = ctx->h_out + (size_t)unit * ctx->out_stride;
+    const float2* o4 = (const float2*)base;
+    const int* ok = (const int*)(o4 + 4 * (size_t)per);
+    const float* oX = (const float*)(ok + per);
+    const int* oi = (const int*)(oX + 3 * (size_t)per);
+    if (pts4) for (int k = 0; k < 4; k++) memcpy(pts4 + (size_t)k * nv, o4 + (size_t)k * per, (size_t)nv * sizeof(float2));
+    if (kept_idx) memcpy(kept_idx, ok, (size_t)nv * sizeof(int));
+    if (X) memcpy(X, oX, (size_t)nv * 3 * sizeof(float));
+    if (inliers) memcpy(inliers, oi, (size_t)ni * sizeof(int));
+    if (d2h_bytes_per_unit) *d2h_bytes_per_unit = ctx->out_stride;
+    return VO_OK;
 }
 
 extern "C" int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,

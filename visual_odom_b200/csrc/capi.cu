@@ -34,7 +34,9 @@ extern "C" int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pts_in, prev_pts, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_npts, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     const int ip[1] = {0}, in[1] = {1};
+    ctx->lk_per_unit = n;
     rc = vo_run_lk(ctx, View{0, 1, ctx->stream}, 1, ip, in, err != nullptr);
+    ctx->lk_per_unit = 0;
     ctx->imgs_per_unit = 4;
     if (rc) return rc;
     VO_CUDA_CHECK(cudaMemcpyAsync(next_pts, ctx->d_pts_out, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -68,7 +70,10 @@ extern "C" int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* 
         VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_ages_in, ages_io, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     // ring order: L0->R0, R0->R1, R1->L1, L1->L0   (planes: L0=0, R0=1, L1=2, R1=3)
     const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};
-    if ((rc = vo_run_lk(ctx, View{0, 1, ctx->stream}, 4, ip, in, false))) return rc;
+    ctx->lk_per_unit = n;
+    rc = vo_run_lk(ctx, View{0, 1, ctx->stream}, 4, ip, in, false);
+    ctx->lk_per_unit = 0;
+    if (rc) return rc;
     if ((rc = vo_run_filter(ctx, View{0, 1, ctx->stream}, ages_io != nullptr))) return rc;
     int n3 = 0;
     VO_CUDA_CHECK(cudaMemcpyAsync(&n3, ctx->d_n3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -137,7 +142,7 @@ extern "C" int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     int rc = ensure_any_state(ctx);
     if (rc) return rc;
-    memcpy(ctx->P_l, P_l, 12 * sizeof(float)); memcpy(ctx->P_r, P_r, 12 * sizeof(float)); ctx->have_P = true;
+    vo_set_calibration(ctx, P_l, P_r);
     const size_t cs = (size_t)ctx->units * ctx->cap;
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4, pts_l, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_valid4 + cs, pts_r, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));

@@ -63,9 +63,13 @@ extern "C" int vo_create(int device, const vo_params* params, vo_ctx** out)
     ctx->stream = ctx->own_stream;
     VO_CUDA_CHECK(vo_lk_prepare());
     ctx->cap = ctx->p.max_features;
+    VO_CUDA_CHECK(cudaMalloc(&ctx->d_lk_queue, LK_QUEUES * 2 * sizeof(int)));
+    VO_CUDA_CHECK(cudaMemset(ctx->d_lk_queue, 0, LK_QUEUES * 2 * sizeof(int)));
     {   // VO_LK_STAGING=ldg switches the LK window staging from TMA to plain loads (debug / A-B runs)
         const char* st = getenv("VO_LK_STAGING");
         ctx->lk_use_tma = !(st && strcmp(st, "ldg") == 0);
+        const char* sp = getenv("VO_LK_SPAN");      // force the LK work-item size (tests run the whole suite at 1)
+        if (sp) ctx->lk_span = atoi(sp);
     }
     return VO_OK;
 }
@@ -92,6 +96,8 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_bgr) cudaFree(ctx->d_bgr);
+    if (ctx->d_lk_queue) cudaFree(ctx->d_lk_queue);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -118,6 +124,10 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (!ctx || !key) return VO_E_INVALID;
     if (strcmp(key, "batch_streams") == 0) { ctx->batch_streams = value >= 2 ? 2 : 1; return VO_OK; }
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
+    if (strcmp(key, "lk_ctas_per_sm") == 0) { ctx->lk_ctas_per_sm = (int)value; vo_drop_graphs(ctx); return VO_OK; }
+    if (strcmp(key, "batch_outputs") == 0) { ctx->batch_outputs = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
+    if (strcmp(key, "lk_span") == 0) { ctx->lk_span = (int)value; vo_drop_graphs(ctx); return VO_OK; }
+    if (strcmp(key, "lk_kernel") == 0) { ctx->lk_kernel = value == 3 ? 3 : 4; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
     if (strcmp(key, "batch_graphs") == 0) { ctx->batch_graphs = value >= 1; return VO_OK; }
     if (strcmp(key, "priorities") == 0) { ctx->use_priorities = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
@@ -173,11 +183,23 @@ void vo_drop_graphs(vo_ctx* ctx)
     ctx->graphs.clear();
 }
 
+void vo_set_calibration(vo_ctx* ctx, const float P_l[12], const float P_r[12])
+{
+    const bool same = ctx->have_P && memcmp(ctx->P_l, P_l, 12 * sizeof(float)) == 0 && memcmp(ctx->P_r, P_r, 12 * sizeof(float)) == 0;
+    if (same) return;
+    // TriArgs / PnpArgs are passed by value: a captured graph would keep replaying the old matrices
+    vo_drop_graphs(ctx);
+    memcpy(ctx->P_l, P_l, 12 * sizeof(float));
+    memcpy(ctx->P_r, P_r, 12 * sizeof(float));
+    ctx->have_P = true;
+}
+
 void vo_free_state(vo_ctx* ctx)
 {
     vo_drop_graphs(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     ctx->allocs.clear();
+    ctx->d_out = nullptr; ctx->out_stride = 0; ctx->out_per = 0;
     ctx->w = ctx->h = ctx->units = 0;
 }
 
@@ -282,6 +304,8 @@ int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int /*imgs_per_unit*/)
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_pts_out, 4 * uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_status, 4 * uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_err, 4 * uc));
+    VO_CUDA_CHECK(dalloc(ctx, &ctx->d_lk_progress, uc));
+    VO_CUDA_CHECK(cudaMemsetAsync(ctx->d_lk_progress, 0, uc * sizeof(int), ctx->stream));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_ages_in, uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_ages_out, uc));
     VO_CUDA_CHECK(dalloc(ctx, &ctx->d_kept5, 5 * uc));
@@ -395,7 +419,25 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         ctx->ev_used += 2;
         VO_CUDA_CHECK(cudaEventRecord(e0, v.s));
     }
-    VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, v.s));
+    if (ctx->lk_kernel == 3) {
+        VO_CUDA_CHECK(vo_launch_lk_ring_v3(ctx->maps, a, v.s));
+    } else {
+        // the queue pair of the launching stream
+        size_t qi = 0;
+        while (qi < ctx->lk_queue_streams.size() && ctx->lk_queue_streams[qi] != v.s) qi++;
+        if (qi == ctx->lk_queue_streams.size()) {
+            if (qi >= LK_QUEUES) { vo_set_error(ctx, "more than %d streams launch the LK kernel", LK_QUEUES); return VO_E_CAPACITY; }
+            ctx->lk_queue_streams.push_back(v.s);
+        }
+        a.queue = ctx->d_lk_queue + 2 * qi;
+        a.per_unit = ctx->lk_per_unit > 0 && ctx->lk_per_unit < ctx->cap ? ctx->lk_per_unit : ctx->cap;
+        a.progress = ctx->d_lk_progress + uo;
+        {   // a launch with fewer features than resident warps gains nothing from splitting its rings
+            const long resident_warps = (long)ctx->sm_count * LK_CTAS_PER_SM * LK_WARPS_PER_CTA;
+            a.span = ctx->lk_span > 0 ? ctx->lk_span : ((long)a.n_units * a.per_unit > resident_warps ? 1 : 0);
+        }
+        VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->sm_count, ctx->lk_ctas_per_sm, v.s));
+    }
     ctx->launches += 1;
     if (e1) VO_CUDA_CHECK(cudaEventRecord(e1, v.s));
     return VO_OK;

@@ -9,6 +9,7 @@
 #include "../../include/vo_b200.h"
 #include <vector>
 #include <stdarg.h>
+#define LK_QUEUES 32
 
 struct vo_ctx {
     int device = 0;
@@ -93,6 +94,16 @@ struct vo_ctx {
     long long lk_n = 0;
     bool lk_timing = true;
     bool lk_use_tma = true;
+    int lk_ctas_per_sm = 0;             // 0 = the default instantiation (LK_CTAS_PER_SM)
+    int lk_span = 0;                    // phases per LK work item: 0 = automatic (one level-solve per item when a launch has
+                                        // more features than resident warps, else one item per feature-ring)
+    int* d_lk_progress = nullptr;       // [units][cap] hand-over counters of the LK work items (zero between launches)
+    int lk_kernel = 4;                  // 3 = the round-1 kernel (A/B measurement only)
+    int lk_per_unit = 0;                // upper bound of live features per unit known to the host (0 = cap)
+    // work queues of the persistent LK warps: one (next, dry) pair per stream that launches the kernel,
+    // so launches of different streams never share a pair; a pair resets itself at the end of a launch
+    int* d_lk_queue = nullptr;          // [LK_QUEUES][2]
+    std::vector<cudaStream_t> lk_queue_streams;
 
     // ---- batched path bookkeeping -----------------------------------------------------------
     int batch_units = 0;            // units configured by vo_batch_configure
@@ -100,7 +111,7 @@ struct vo_ctx {
     bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
     int batch_streams = 2;          // unit ranges run concurrently by the batched path
     bool use_graphs = true;         // replay the per-range kernel sequence as a CUDA graph (no LK event timing then)
-    struct RangeGraph { int u0, n; bool detect, tma; cudaGraphExec_t exec; long long launches; };
+    struct RangeGraph { int u0, n; bool detect, tma; cudaStream_t s; cudaGraphExec_t exec; long long launches; };   // s: the stream it was captured on (its LK work queue is that stream's)
     std::vector<RangeGraph> graphs; // invalidated when the device state is re-allocated
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
     cudaStream_t hi_stream[2] = {nullptr, nullptr};     // high-priority helpers of the side streams (see run_range_launch)
@@ -111,6 +122,13 @@ struct vo_ctx {
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     struct Pending { int u0 = 0, n = 0; bool active = false; cudaEvent_t done = nullptr; };
     std::vector<Pending> pending;   // vo_batch_submit / vo_batch_wait
+    // full outputs of a submission (what matchingFeatures / trackingFrame2Frame hand back): packed per unit on the
+    // device and copied with ONE D2H per submission into pinned staging (vo_set_option "batch_outputs")
+    bool batch_outputs = false;
+    uint8_t* d_out = nullptr;       // [units][out_stride]  (part of the batch state)
+    uint8_t* h_out = nullptr;       // pinned, [out_units][out_stride]
+    size_t out_stride = 0;
+    int out_per = 0, out_units = 0; // point slots per unit in a packed block; units the pinned block holds
     unsigned submit_count = 0;
 };
 
@@ -118,6 +136,8 @@ void vo_set_error(vo_ctx* ctx, const char* fmt, ...);
 int vo_ensure_state(vo_ctx* ctx, int w, int h, int units, int imgs_per_unit);
 void vo_free_state(vo_ctx* ctx);
 void vo_drop_graphs(vo_ctx* ctx);
+// new projection matrices: cached graphs carry the old calibration in their kernel arguments, so they are dropped
+void vo_set_calibration(vo_ctx* ctx, const float P_l[12], const float P_r[12]);
 int vo_drain_pending(vo_ctx* ctx);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);

@@ -2,8 +2,10 @@
 #pragma once
 #include "common.cuh"
 
-#define LK_WARPS_PER_CTA 1
-#define LK_MIN_CTAS_PER_SM 17
+// Resident warps per SM the kernel is built for: 12 persistent CTAs of 2 warps (<= 80 registers per thread,
+// 8960 B of shared memory per warp: 12 x (2 x 8960 + 1024 reserved) = 227 328 B of the SM's 233 472 B).
+#define LK_WARPS_PER_CTA 2
+#define LK_CTAS_PER_SM 12
 
 struct LkMaps {
     CUtensorMap img_i[VO_MAX_LEVELS];  // u8 planes, box 48 x 22 x 1 (I window, 16-byte aligned start)
@@ -30,6 +32,12 @@ struct LkArgs {
     uint8_t* status_out;    // [ncalls][n_units][cap]
     float* err_out;         // optional, same shape
     size_t call_stride;
+    // work queue of the persistent warps: queue[0] = next item, queue[1] = warps that ran dry (the last one
+    // resets both, so the pair is clean for the next launch that uses it); items = n_units * per_unit
+    int* queue;
+    int per_unit;           // feature slots per unit that can be live (<= cap)
+    int span;               // phases (level-solves) per work item; 0 or >= ncalls*nlevels = one item per feature-ring
+    int* progress;          // [n_units][cap] phases completed per feature (hand-over between items; all zero between launches)
     // plain-load staging (debug / A-B measurement; VO_LK_STAGING=ldg): plane geometry per level
     int use_tma;
     const uint8_t* img_base[VO_MAX_LEVELS];
@@ -40,5 +48,10 @@ struct LkArgs {
 
 size_t vo_lk_smem_bytes();
 cudaError_t vo_lk_prepare();
-cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
+// sm_count sizes the persistent grid (CTAs = min(needed, sm_count * LK_CTAS_PER_SM))
+// ctas_per_sm: 0 = LK_CTAS_PER_SM; 10 / 8 select the instantiations built with more registers (A/B measurement)
+cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream);
+// round-1 kernel (one single-warp CTA per feature), kept for A/B measurement only
+cudaError_t vo_lk_prepare_v3();
+cudaError_t vo_launch_lk_ring_v3(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
 int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch, cudaStream_t stream);

@@ -79,7 +79,13 @@ static int seq_front(vo_ctx* ctx, int s0, int s1, int unit, bool bgr)
     ctx->launches += vo_launch_seq_append(a, ctx->stream);
     ctx->launches += vo_launch_seq_bucket(a, ctx->stream);
     const int ip[4] = {L0, R0, R1, L1}, in[4] = {R0, R1, L1, L0};
-    if ((rc = vo_run_lk_ring(ctx, v, 4, ip, in, false))) return rc;
+    {   // bucketingFeatures() reads back (rows/bs + 1) x (cols/bs + 1) slots at most (feature.cpp:242-249)
+        const int bs = ctx->h / 10 > 0 ? ctx->h / 10 : 1;
+        ctx->lk_per_unit = (ctx->h / bs + 1) * (ctx->w / bs + 1);
+    }
+    rc = vo_run_lk_ring(ctx, v, 4, ip, in, false);
+    ctx->lk_per_unit = 0;
+    if (rc) return rc;
     if ((rc = vo_run_filter(ctx, v, true))) return rc;
     // state carry: features.points = pointsLeft_t1, ages keep their A3 length
     ctx->launches += vo_launch_seq_carry(a, ctx->stream);
@@ -111,7 +117,7 @@ static int seq_graph(vo_ctx* ctx, int key, cudaStream_t st, F launch)
 {
     if (!ctx->use_graphs) return launch();
     for (auto& g : ctx->graphs)
-        if (g.u0 == key && g.tma == ctx->lk_use_tma) {
+        if (g.u0 == key && g.tma == ctx->lk_use_tma && g.s == st) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
             ctx->launches += g.launches;
             return VO_OK;
@@ -127,7 +133,7 @@ static int seq_graph(vo_ctx* ctx, int key, cudaStream_t st, F launch)
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     VO_CUDA_CHECK(e);
     vo_ctx::RangeGraph g;
-    g.u0 = key; g.n = 1; g.detect = true; g.tma = ctx->lk_use_tma;
+    g.u0 = key; g.n = 1; g.detect = true; g.tma = ctx->lk_use_tma; g.s = st;
     g.launches = ctx->launches - before;
     VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
@@ -185,9 +191,7 @@ extern "C" int vo_seq_begin_ex(vo_ctx* ctx, int w, int h, const float P_l[12], c
     if ((rc = vo_ensure_state(ctx, w, h, 2, 4))) return rc;          // two per-frame buffer units (frames in flight)
     if ((rc = seq_events(ctx))) return rc;
     if ((rc = vo_ensure_pinned(ctx, 2 * sizeof(SeqRecord) + 256))) return rc;
-    memcpy(ctx->P_l, P_l, 12 * sizeof(float));
-    memcpy(ctx->P_r, P_r, 12 * sizeof(float));
-    ctx->have_P = true;
+    vo_set_calibration(ctx, P_l, P_r);
     ctx->imgs_per_unit = 4;
     ctx->seq_slot = 0;
     ctx->seq_frames = 0;

@@ -62,3 +62,79 @@ def gather_records(local_records, local_unit_ids, n_units, device="cpu"):
     table[ids] = rows[:, 1:]
     assert len(np.unique(ids)) == n_units, "some units were not processed by any rank"
     return table
+
+
+class AsyncRecordGather:
+    """Non-blocking form of gather_records for a pipelined loop: every post() stages the rank's records in pinned
+    memory and enqueues H2D -> all_gather -> D2H on a side stream; nothing waits until the ring of `depth` slots wraps
+    or drain() is called.  Tables come back in posting order."""
+
+    def __init__(self, n_units, device="cuda", depth=4):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_units = n_units
+        self.per = (n_units + self.world - 1) // self.world
+        self.device = device
+        cuda = str(device).startswith("cuda")
+        self.side = torch.cuda.Stream() if cuda else None
+        self.slots = []
+        for _ in range(depth):
+            h_in = torch.zeros((self.per, RECORD_LEN + 1), dtype=torch.float64, pin_memory=cuda)
+            h_out = torch.zeros((self.world * self.per, RECORD_LEN + 1), dtype=torch.float64, pin_memory=cuda)
+            self.slots.append(dict(h_in=h_in, h_out=h_out, d_in=torch.zeros_like(h_in, device=device),
+                                   d_out=torch.zeros_like(h_out, device=device),
+                                   ev=torch.cuda.Event() if cuda else None, busy=False))
+        self.k = 0
+        self.tables = []
+
+    def _harvest(self, s):
+        if s["ev"] is not None:
+            s["ev"].synchronize()
+        rows = s["h_out"].numpy()
+        rows = rows[rows[:, 0] >= 0]
+        table = np.zeros((self.n_units, RECORD_LEN), np.float64)
+        ids = rows[:, 0].astype(np.int64)
+        table[ids] = rows[:, 1:]
+        assert len(np.unique(ids)) == self.n_units, "some units were not processed by any rank"
+        self.tables.append(table)
+        s["busy"] = False
+
+    def post(self, local_records, local_unit_ids):
+        torch, dist = self.torch, self.dist
+        s = self.slots[self.k % len(self.slots)]
+        self.k += 1
+        if s["busy"]:
+            self._harvest(s)
+        h = s["h_in"].numpy()
+        h[:, 0] = -1
+        n = len(local_unit_ids)
+        if n:
+            h[:n, 0] = np.asarray(local_unit_ids, np.float64)
+            h[:n, 1:] = np.asarray(local_records, np.float64).reshape(n, RECORD_LEN)
+        if self.side is not None:
+            with torch.cuda.stream(self.side):
+                s["d_in"].copy_(s["h_in"], non_blocking=True)
+                if self.world > 1:
+                    dist.all_gather_into_tensor(s["d_out"], s["d_in"])
+                else:
+                    s["d_out"].copy_(s["d_in"])
+                s["h_out"].copy_(s["d_out"], non_blocking=True)
+                s["ev"].record(self.side)
+        else:
+            if self.world > 1:
+                dist.all_gather_into_tensor(s["d_out"], s["d_in"].copy_(s["h_in"]))
+            else:
+                s["d_out"].copy_(s["h_in"])
+            s["h_out"].copy_(s["d_out"])
+        s["busy"] = True
+
+    def drain(self):
+        n = len(self.slots)
+        for i in range(self.k - min(self.k, n), self.k):        # oldest first
+            s = self.slots[i % n]
+            if s["busy"]:
+                self._harvest(s)
+        out, self.tables = self.tables, []
+        return out
