@@ -15,9 +15,8 @@ public:
     Frame(int frameId, const cv::Mat projMatL, const cv::Mat projMatR, cv::Mat worldRotation, cv::Mat worldTranslation);
 
     void setFeatures(std::vector<cv::Point2f> left, std::vector<cv::Point2f> right);
-    // cv::triangulatePoints(m_projMatL, m_projMatR, left, right, points4D) in the reference returns a
-    // unit-norm homogeneous 4 x N CV_32F matrix of arbitrary sign; here the same points come back
-    // de-homogenised as (x, y, z, 1) -- see INTEGRATION.md.
+    // cv::triangulatePoints(m_projMatL, m_projMatR, left, right, points4D): points4D = 4 x N CV_32F, column i the
+    // unit-norm homogeneous point of feature i -- the same bits OpenCV's per-point SVD produces (reference src/Frame.cpp:25-28).
     void triangulateFeaturePoints(cv::Mat& points4D);
 };
 #endif

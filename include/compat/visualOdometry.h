@@ -6,6 +6,7 @@
 
 #include "feature.h"
 #include "bucket.h"
+#include "utils.h"       // as the reference does (src/visualOdometry.h:22)
 #include "Frame.h"
 
 // FAST refill (< 2000 features) -> bucketing (rows/10, 1 per bucket) -> circular matching -> 1-px
@@ -16,8 +17,9 @@ void matchingFeatures(cv::Mat& imageLeft_t0, cv::Mat& imageRight_t0, cv::Mat& im
 
 // solvePnPRansac(500 / 0.5 px / 0.999, ITERATIVE, extrinsic guess = translation) + Rodrigues.
 // `translation` is in/out (3x1 CV_64F), `rotation` out (3x3 CV_64F).            src/visualOdometry.cpp:132-193
-// mono_rotation = true selects the reference's 5-point essential-matrix branch, which its main() never
-// takes (src/main.cpp:181) and which is not built here: it throws std::runtime_error.
+// mono_rotation = true (the header default, as in the reference; its main() passes false, src/main.cpp:181): `rotation`
+// comes from findEssentialMat(RANSAC, 0.999, 1.0) + recoverPose on (pointsLeft_t0, pointsLeft_t1) (:146-157), the PnP then
+// only updates `translation`.
 void trackingFrame2Frame(cv::Mat& projMatrl, cv::Mat& projMatrr, Points& pointsLeft_t0, Points& pointsLeft_t1,
                          cv::Mat& points3D_t0, cv::Mat& rotation, cv::Mat& translation, bool mono_rotation = true);
 

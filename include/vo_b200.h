@@ -38,6 +38,9 @@ extern "C" {
 #define VO_E_CUDA (-2)           /* CUDA runtime/driver failure (text in vo_last_error)      */
 #define VO_E_TOO_FEW_POINTS (-3) /* PnP with < 4 points (the reference aborts in cv::solvePnPRansac) */
 #define VO_E_UNSUPPORTED (-4)    /* parameter outside what the kernels are built for         */
+/* pnp_status only: RANSAC found no model with more than 4 inliers; the pose is what the reference is left with when it
+ * ignores cv::solvePnPRansac's return value: R = I (rvec stays 0), t = the caller's guess */
+#define VO_PNP_NO_MODEL 1
 #define VO_E_CAPACITY (-5)       /* caller buffer / context capacity too small               */
 
 typedef struct vo_ctx vo_ctx;
@@ -117,6 +120,11 @@ VO_API int vo_circular_match(vo_ctx* ctx, const uint8_t* l0, const uint8_t* r0, 
  * src/Frame.cpp:25-28).  P_l, P_r: row-major 3x4 float (CV_32F, main.cpp:73-74). */
 VO_API int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[12], const vo_point2f* pts_l,
                           const vo_point2f* pts_r, int n, vo_point3f* X);
+/* The same triangulation, returned the way cv::triangulatePoints itself returns it (Frame::triangulateFeaturePoints,
+ * reference src/Frame.cpp:25-28): X4 = n x 4 floats, point i = the unit-norm homogeneous vector (x, y, z, w) that is
+ * column i of OpenCV's 4 x N CV_32F output (same bits, same sign). */
+VO_API int vo_triangulate_homogeneous(vo_ctx* ctx, const float P_l[12], const float P_r[12], const vo_point2f* pts_l,
+                                      const vo_point2f* pts_r, int n, float* X4);
 
 /* ---- A9: cv::solvePnPRansac(..., SOLVEPNP_ITERATIVE, useExtrinsicGuess) + cv::Rodrigues --------
  * replaces the pose solve of trackingFrame2Frame(), reference src/visualOdometry.cpp:161-189.
@@ -129,6 +137,16 @@ VO_API int vo_triangulate(vo_ctx* ctx, const float P_l[12], const float P_r[12],
 VO_API int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f* x, int n, const float K[9],
                          double rvec_io[3], double tvec_io[3], int32_t* inliers, int* n_inliers,
                          double R_out[9], int* ransac_iters /* optional */);
+
+/* ---- N5: the mono_rotation = true branch of trackingFrame2Frame (the header default of the reference's flag) -------
+ * replaces reference src/visualOdometry.cpp:146-157:
+ *     E = cv::findEssentialMat(pointsLeft_t0, pointsLeft_t1, focal, pp, cv::RANSAC, 0.999, 1.0, mask);
+ *     cv::recoverPose(E, pointsLeft_t0, pointsLeft_t1, rotation, translation_mono, focal, pp, mask);
+ * Five-point RANSAC (1000 iterations at most, adaptive bound) + the four-way cheirality vote.  R_out = `rotation`
+ * (row-major 3x3); mask_out (optional, n bytes) = inliers of the best E; *n_inliers their count.
+ * n < 5 or no model: VO_E_TOO_FEW_POINTS (OpenCV throws in both cases). */
+VO_API int vo_mono_rotation(vo_ctx* ctx, const vo_point2f* pts_t0, const vo_point2f* pts_t1, int n, double focal, double ppx,
+                            double ppy, double R_out[9], uint8_t* mask_out, int* n_inliers, int* ransac_iters);
 
 /* ---- batched whole-path API (configs 4/5 of BASELINE.json, bench.py, multi-GPU sharding) ------
  * One work unit = one stereo pair-of-pairs + its feature list (SURVEY.md section 8d "Work unit").
@@ -149,7 +167,7 @@ typedef struct vo_unit_result {
     int n_valid;         /* survivors of checkValidMatch/removeInvalidPoints (A5/A6)   */
     int n_inliers;       /* RANSAC inliers                                             */
     int ransac_iters;    /* iterations the adaptive loop ran                           */
-    int pnp_status;      /* VO_OK or VO_E_TOO_FEW_POINTS                               */
+    int pnp_status;      /* VO_OK, VO_PNP_NO_MODEL, VO_E_TOO_FEW_POINTS (n < 4) or VO_E_UNSUPPORTED (n == 4: P3P) */
     double rvec[3], tvec[3], R[9];
 } vo_unit_result;
 

@@ -4,7 +4,9 @@
 //   in : int32 w, h, n_frames ; float P_l[12], P_r[12] ; then n_frames x (left, right) u8 images
 //   out: per processed frame pair: int32 n ; n x (pL0, pR0, pL1, pR1) float2 ; n x float3 X ;
 //        int32 n_inl ; n_inl x int32 ; double R[9] ; double t[3] ; int32 n_features_after (currentVOFeatures) ;
-//        double frame_pose[16] after the Euler gate + integrateOdometryStereo (reference src/main.cpp:196-208)
+//        double frame_pose[16] after the Euler gate + integrateOdometryStereo (reference src/main.cpp:196-208) ;
+//        4 x n float: Frame::triangulateFeaturePoints of (pL0, pR0) (reference src/Frame.cpp:25-28) ;
+//        double R_mono[9], t_mono[3]: the same trackingFrame2Frame call with the flag's header default (mono_rotation = true)
 #include "visualOdometry.h"
 #include "utils.h"
 #include <cmath>
@@ -41,6 +43,7 @@ int main(int argc, char** argv)
         imageLeft_t0 = imageLeft_t1; imageRight_t0 = imageRight_t1;
         cv::Mat points3D_t0;
         triangulateStereo(projMatrl, projMatrr, pointsLeft_t0, pointsRight_t0, points3D_t0);
+        cv::Mat rot_mono = cv::Mat::eye(3, 3, CV_64FC1), tr_mono = translation.clone();
         trackingFrame2Frame(projMatrl, projMatrr, pointsLeft_t0, pointsLeft_t1, points3D_t0, rotation, translation, false);
         const int32_t n = (int32_t)pointsLeft_t0.size();
         std::fwrite(&n, 4, 1, fo);
@@ -58,6 +61,14 @@ int main(int argc, char** argv)
         if (std::fabs(e[1]) < 0.1 && std::fabs(e[0]) < 0.1 && std::fabs(e[2]) < 0.1)
             integrateOdometryStereo(frame_id, rigid_body_transformation, frame_pose, rotation, translation);
         std::fwrite(frame_pose.data, 8, 16, fo);
+        Frame fr(frame_id, projMatrl, projMatrr, rotation, translation);       // the reference's (otherwise unused) holder class
+        fr.setFeatures(pointsLeft_t0, pointsRight_t0);
+        cv::Mat points4D;
+        fr.triangulateFeaturePoints(points4D);
+        for (int r = 0; r < 4; r++) std::fwrite(points4D.ptr<float>(r), 4, n, fo);
+        // a caller that omits the flag gets the reference's default, mono_rotation = true (src/visualOdometry.h:42)
+        trackingFrame2Frame(projMatrl, projMatrr, pointsLeft_t0, pointsLeft_t1, points3D_t0, rot_mono, tr_mono);
+        std::fwrite(rot_mono.data, 8, 9, fo); std::fwrite(tr_mono.data, 8, 3, fo);
     }
     std::fclose(fi); std::fclose(fo);
     return 0;

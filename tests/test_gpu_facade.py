@@ -70,4 +70,15 @@ def test_facade_sequence_matches_reference(built, tmp_path):
         frame_pose = ref_path.integrate_pose(frame_pose, R, translation)
         pose_g = take(np.float64, 16).reshape(4, 4)
         assert np.abs(pose_g - frame_pose).max() <= 1e-9 * max(1.0, np.abs(frame_pose).max())
+        # Frame::triangulateFeaturePoints == cv::triangulatePoints: 4 x N unit-norm homogeneous columns, bit for bit
+        import cv2
+        X4 = cv2.triangulatePoints(base["P_l"], base["P_r"], pL0.T.copy(), pR0.T.copy())
+        assert np.array_equal(take(np.float32, 4 * n).reshape(4, n), X4)
+        # the flag's default (mono_rotation = true): rotation from the five-point branch, translation from the same PnP
+        focal = float(base["P_l"][0, 0]); pp = (float(base["P_l"][0, 2]), float(base["P_l"][1, 2]))
+        E, emask = cv2.findEssentialMat(pL0, pL1, focal, pp, cv2.RANSAC, 0.999, 1.0)
+        _, R_m, _t, _ = cv2.recoverPose(E, pL0, pL1, focal=focal, pp=pp, mask=emask.copy())
+        Rm_g = take(np.float64, 9).reshape(3, 3); tm_g = take(np.float64, 3)
+        assert np.linalg.norm(Rm_g - R_m) <= 1e-4 * np.linalg.norm(R_m), f"frame {k}: mono rotation"
+        assert np.array_equal(tm_g, tg), f"frame {k}: the PnP translation does not depend on the flag"
         assert n > 100 and ni > 50

@@ -104,3 +104,62 @@ def test_pipelined_submit_wait_equals_push(ctx):
         ctx.seq_push(frames[2][0], frames[2][1])
     check(ctx.seq_wait(), 0)
     check(ctx.seq_push(frames[2][0], frames[2][1]), 1)
+
+
+def test_new_calibration_on_a_used_context_equals_a_fresh_context(built):
+    """The frame graphs carry the projection matrices in their kernel arguments: a second sequence (and a batch) on the
+    SAME context with the same image size but another calibration must not replay the old matrices."""
+    from visual_odom_b200.capi import Context
+    w, h, nf = 640, 240, 4
+    base, frames = _frames(w, h, 13, nf)
+    P_l2, P_r2 = base["P_l"].copy(), base["P_r"].copy()
+    P_l2[0, 0] *= 1.07; P_l2[1, 1] *= 1.07; P_r2[0, 0] *= 1.07; P_r2[1, 1] *= 1.07; P_r2[0, 3] *= 1.2     # focal length / baseline
+
+    def run(c, P_l, P_r):
+        c.seq_begin(frames[0][0], frames[0][1], P_l, P_r)
+        return [c.seq_push(l, r) for l, r in frames[1:]]
+
+    used = Context(0, max_features=2048)
+    first = run(used, base["P_l"], base["P_r"])           # captures the graphs with the first calibration
+    second = run(used, P_l2, P_r2)
+    fresh = Context(0, max_features=2048)
+    want = run(fresh, P_l2, P_r2)
+    for a, b in zip(second, want):
+        assert a["n_inliers"] == b["n_inliers"] and np.array_equal(a["tvec"], b["tvec"]) and np.array_equal(a["R"], b["R"])
+    assert any(not np.array_equal(a["tvec"], b["tvec"]) for a, b in zip(first, second))      # the calibration matters
+    # the batched path caches graphs per unit range too
+    u = dict(l0=frames[0][0], r0=frames[0][1], l1=frames[1][0], r1=frames[1][1])
+    outs = []
+    for c, cals in ((used, [(base["P_l"], base["P_r"]), (P_l2, P_r2)]), (fresh, [(P_l2, P_r2)])):
+        for P_l, P_r in cals:
+            c.batch_configure(w, h, 1, P_l, P_r)
+            arr, keep, pitch = c.make_units([dict(u, n_select=300, t_prev=(0.0, 0.0, -0.2))])
+            outs.append(c.frame_batch(arr, pitch)[0])
+    assert np.array_equal(outs[1]["tvec"], outs[2]["tvec"]) and outs[1]["n_inliers"] == outs[2]["n_inliers"]
+    assert not np.array_equal(outs[0]["tvec"], outs[1]["tvec"])
+    used.close(); fresh.close()
+
+
+def test_host_buffer_calls_do_not_corrupt_a_sequence(built):
+    """Entry points that reuse the sequence's image planes are refused while a frame is in flight, and end an idle
+    sequence instead of silently corrupting it."""
+    from visual_odom_b200.capi import Context
+    w, h = 640, 240
+    base, frames = _frames(w, h, 17, 4)
+    c = Context(0, max_features=2048)
+    c.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])
+    c.seq_submit(frames[1][0], frames[1][1])
+    pts = np.array([[100.5, 80.25], [300.0, 120.0]], np.float32)
+    with pytest.raises(RuntimeError, match="have not been waited for"):
+        c.lk_track(frames[0][0], frames[1][0], pts)
+    with pytest.raises(RuntimeError, match="have not been waited for"):
+        c.fast_detect(frames[0][0])
+    r1 = c.seq_wait()
+    assert r1["n_valid"] > 20
+    c.lk_track(frames[0][0], frames[1][0], pts)           # idle sequence: allowed, and the sequence is over
+    with pytest.raises(RuntimeError):
+        c.seq_push(frames[2][0], frames[2][1])
+    c.seq_begin(frames[0][0], frames[0][1], base["P_l"], base["P_r"])      # a new sequence works as before
+    r1b = c.seq_push(frames[1][0], frames[1][1])
+    assert r1b["n_inliers"] == r1["n_inliers"] and np.array_equal(r1b["tvec"], r1["tvec"])
+    c.close()

@@ -48,6 +48,10 @@ def test_triangulate_bit_exact(ctx):
     X4 = cv2.triangulatePoints(P_l, P_r, a.T.copy(), b.T.copy())
     Xc = cv2.convertPointsFromHomogeneous(X4.T.copy()).reshape(-1, 3)
     assert np.array_equal(X, Xc)
+    # the homogeneous form itself (what Frame::triangulateFeaturePoints returns, reference src/Frame.cpp:25-28):
+    # same bits, same sign as cv2's unit-norm columns
+    H = ctx.triangulate_homogeneous(P_l, P_r, a, b)
+    assert np.array_equal(H, X4.T)
 
 
 @pytest.mark.parametrize("n,sigma,outl,seed", [(1500, 0.05, 0.1, 0), (1500, 0.15, 0.3, 1), (1500, 0.2, 0.5, 2),
@@ -76,3 +80,23 @@ def test_pnp_small_counts(ctx):
     with pytest.raises(VoError) as e:
         ctx.pnp_ransac(X[:4], x[:4], K)
     assert e.value.code == VO_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n,sigma,outl,seed", [(300, 0.1, 0.1, 0), (500, 0.2, 0.3, 1), (1000, 0.3, 0.5, 2), (200, 0.05, 0.0, 3),
+                                              (60, 0.2, 0.2, 4), (1500, 0.15, 0.3, 5), (800, 0.25, 0.6, 6), (2000, 0.1, 0.2, 7)])
+def test_mono_rotation_matches_cv2(ctx, n, sigma, outl, seed):
+    """Row N5: findEssentialMat(RANSAC, 0.999, 1.0) + recoverPose (reference src/visualOdometry.cpp:146-157) on the GPU
+    against cv2: the essential-matrix inlier mask is identical and the rotation agrees to 1e-4 relative (in fact 1e-8)."""
+    cv2 = pytest.importorskip("cv2")
+    p0, p1, focal, pp = synth.essential_stress_set(n, sigma, outl, seed)
+    E, mask = cv2.findEssentialMat(p0, p1, focal, pp, cv2.RANSAC, 0.999, 1.0)
+    _, R, t, _ = cv2.recoverPose(E, p0, p1, focal=focal, pp=pp, mask=mask.copy())
+    Rg, mg, iters = ctx.mono_rotation(p0, p1, focal, pp)
+    assert np.array_equal(mg, mask.ravel().astype(bool))
+    assert np.linalg.norm(Rg - R) <= 1e-4 * np.linalg.norm(R)
+    assert 1 <= iters <= 1000
+
+
+def test_mono_rotation_too_few_points(ctx):
+    with pytest.raises(RuntimeError, match="5 points"):
+        ctx.mono_rotation(np.zeros((4, 2), np.float32), np.zeros((4, 2), np.float32), 700.0, (600.0, 180.0))

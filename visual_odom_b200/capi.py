@@ -64,6 +64,7 @@ SIGNATURES = {
                                     C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int)]),
     "vo_triangulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vo_triangulate_homogeneous": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vo_pnp_ransac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]),
     "vo_batch_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -99,6 +100,8 @@ SIGNATURES = {
     "vo_pose_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vo_seq_pose": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vo_mono_rotation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                   C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vo_batch_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
 }
 
@@ -253,6 +256,25 @@ class Context:
         X = np.zeros((len(a), 3), np.float32)
         self._check(self.lib.vo_triangulate(self.h, _p(P_l), _p(P_r), _p(a), _p(b), len(a), _p(X)))
         return X
+
+    def triangulate_homogeneous(self, P_l, P_r, pts_l, pts_r):
+        """(n, 4) float32: row i = column i of cv2.triangulatePoints' 4 x N output."""
+        P_l = np.ascontiguousarray(P_l, np.float32).reshape(12); P_r = np.ascontiguousarray(P_r, np.float32).reshape(12)
+        a = np.ascontiguousarray(pts_l, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts_r, np.float32).reshape(-1, 2)
+        assert len(a) == len(b)
+        X4 = np.zeros((len(a), 4), np.float32)
+        self._check(self.lib.vo_triangulate_homogeneous(self.h, _p(P_l), _p(P_r), _p(a), _p(b), len(a), _p(X4)))
+        return X4
+
+    def mono_rotation(self, pts_t0, pts_t1, focal, pp):
+        """findEssentialMat(RANSAC, 0.999, 1.0) + recoverPose: (R 3x3, inlier mask, RANSAC iterations)."""
+        a = np.ascontiguousarray(pts_t0, np.float32).reshape(-1, 2); b = np.ascontiguousarray(pts_t1, np.float32).reshape(-1, 2)
+        assert len(a) == len(b)
+        R = np.zeros(9, np.float64); mask = np.zeros(max(len(a), 1), np.uint8)
+        ni = C.c_int(0); it = C.c_int(0)
+        self._check(self.lib.vo_mono_rotation(self.h, _p(a), _p(b), len(a), float(focal), float(pp[0]), float(pp[1]), _p(R), _p(mask),
+                                              C.byref(ni), C.byref(it)))
+        return R.reshape(3, 3), mask[:len(a)].astype(bool), it.value
 
     def pnp_ransac(self, X, x, K, rvec0=None, tvec0=None):
         X = np.ascontiguousarray(X, np.float32).reshape(-1, 3); x = np.ascontiguousarray(x, np.float32).reshape(-1, 2)

@@ -71,8 +71,9 @@ extern "C" int vo_batch_configure(vo_ctx* ctx, int w, int h, int n_units, const 
     if (!ctx) return VO_E_INVALID;
     if (!P_l || !P_r || n_units <= 0) { vo_set_error(ctx, "bad argument"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    int rc = vo_ensure_state(ctx, w, h, n_units, 4);
+    int rc = vo_claim_buffers(ctx, "vo_batch_configure");
     if (rc) return rc;
+    if ((rc = vo_ensure_state(ctx, w, h, n_units, 4))) return rc;
     vo_set_calibration(ctx, P_l, P_r);
     ctx->batch_units = n_units;
     ctx->batch_uploaded = 0;
@@ -141,6 +142,7 @@ extern "C" int vo_batch_upload(vo_ctx* ctx, const vo_unit* units, int n_units, s
     int rc = validate_units(ctx, units, n_units, pitch, &detect, &max_pts);
     if (rc) return rc;
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = vo_claim_buffers(ctx, "vo_batch_upload", true))) return rc;
     if ((rc = vo_drain_pending(ctx))) return rc;
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // staging block may still be in flight
     if ((rc = upload_range(ctx, units, 0, n_units, pitch, ctx->stream, detect))) return rc;
@@ -270,6 +272,7 @@ extern "C" int vo_batch_run(vo_ctx* ctx)
     const int units = ctx->batch_uploaded;
     if (units <= 0) { vo_set_error(ctx, "vo_batch_run: nothing uploaded"); return VO_E_INVALID; }
     if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_run: projection matrices not set"); return VO_E_INVALID; }
+    { int rcc = vo_claim_buffers(ctx, "vo_batch_run"); if (rcc) return rcc; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (units < 2 || ctx->batch_streams < 2) return run_range(ctx, View{0, units, ctx->stream});
     // two unit ranges on two side streams: the latency-bound PnP kernels of one range run under the
@@ -311,6 +314,7 @@ extern "C" int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, si
     if (!results) return VO_E_INVALID;
     if (!ctx->have_P) { vo_set_error(ctx, "vo_frame_batch: projection matrices not set"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if ((rc = vo_claim_buffers(ctx, "vo_frame_batch", true))) return rc;
     if ((rc = vo_drain_pending(ctx))) return rc;
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->batch_uploaded = n_units; ctx->batch_detect = detect; ctx->batch_max_pts = max_pts;
@@ -354,6 +358,7 @@ extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit
         return VO_E_INVALID;
     }
     if (!ctx->have_P) { vo_set_error(ctx, "vo_batch_submit: projection matrices not set"); return VO_E_INVALID; }
+    { int rcc = vo_claim_buffers(ctx, "vo_batch_submit", true); if (rcc) return rcc; }
     for (auto& p : ctx->pending)
         if (p.active && first_unit < p.u0 + p.n && p.u0 < first_unit + n_units) {
             vo_set_error(ctx, "vo_batch_submit: slots [%d, %d) overlap a submission that has not been waited for", first_unit, first_unit + n_units);

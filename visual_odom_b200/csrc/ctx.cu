@@ -97,6 +97,7 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->d_bgr) cudaFree(ctx->d_bgr);
     if (ctx->d_lk_queue) cudaFree(ctx->d_lk_queue);
+    if (ctx->d_ess) cudaFree(ctx->d_ess);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -160,6 +161,22 @@ int vo_ensure_pinned(vo_ctx* ctx, size_t bytes)
     if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; }
     VO_CUDA_CHECK(cudaMallocHost(&ctx->h_pinned, bytes));
     ctx->h_pinned_bytes = bytes;
+    return VO_OK;
+}
+
+int vo_claim_buffers(vo_ctx* ctx, const char* who, bool allow_pending_batches)
+{
+    if (ctx->seq_inflight > 0) {
+        vo_set_error(ctx, "%s: %d frame(s) submitted with vo_seq_submit have not been waited for (this call would overwrite their buffers)", who, ctx->seq_inflight);
+        return VO_E_INVALID;
+    }
+    if (!allow_pending_batches)
+        for (auto& p : ctx->pending)
+            if (p.active) {
+                vo_set_error(ctx, "%s: the vo_batch_submit submission of slots [%d, %d) has not been waited for", who, p.u0, p.u0 + p.n);
+                return VO_E_INVALID;
+            }
+    ctx->seq_active = false;        // the sequence's image planes and per-frame buffers are reused from here on: vo_seq_begin again
     return VO_OK;
 }
 
@@ -433,7 +450,7 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         a.per_unit = ctx->lk_per_unit > 0 && ctx->lk_per_unit < ctx->cap ? ctx->lk_per_unit : ctx->cap;
         a.progress = ctx->d_lk_progress + uo;
         {   // a launch with fewer features than resident warps gains nothing from splitting its rings
-            const long resident_warps = (long)ctx->sm_count * LK_CTAS_PER_SM * LK_WARPS_PER_CTA;
+            const long resident_warps = (long)ctx->sm_count * vo_lk_ctas_per_sm(ctx->lk_ctas_per_sm) * LK_WARPS_PER_CTA;
             a.span = ctx->lk_span > 0 ? ctx->lk_span : ((long)a.n_units * a.per_unit > resident_warps ? 1 : 0);
         }
         VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->sm_count, ctx->lk_ctas_per_sm, v.s));
@@ -499,12 +516,12 @@ int vo_run_select(vo_ctx* ctx, const View& v)
     return VO_OK;
 }
 
-int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n)
+int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n, float4* X4)
 {
     const size_t uo = (size_t)v.u0 * ctx->cap;
     TriArgs t;
     memset(&t, 0, sizeof(t));
-    t.cap = ctx->cap; t.n_pts = n + v.u0; t.pts_l = pts_l + uo; t.pts_r = pts_r + uo; t.X = ctx->d_X + uo;
+    t.cap = ctx->cap; t.n_pts = n + v.u0; t.pts_l = pts_l + uo; t.pts_r = pts_r + uo; t.X = ctx->d_X + uo; t.X4 = X4;
     for (int k = 0; k < 12; k++) { t.Pl[k] = (double)ctx->P_l[k]; t.Pr[k] = (double)ctx->P_r[k]; }
     ctx->launches += vo_launch_triangulate(t, v.n, v.s);
     VO_CUDA_CHECK(cudaGetLastError());

@@ -6,6 +6,7 @@
 #include "fast.h"
 #include "pnp.h"
 #include "seq.h"
+#include "ess.h"
 #include "../../include/vo_b200.h"
 #include <vector>
 #include <stdarg.h>
@@ -81,6 +82,9 @@ struct vo_ctx {
     double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
     uint8_t* d_bgr = nullptr;           // staging of colour (BGR) inputs, converted by k_bgr_to_gray (ingest.cu)
     size_t bgr_bytes = 0;
+    // mono_rotation branch (ess.cu): scratch of the essential-matrix RANSAC, allocated on first use
+    void* d_ess = nullptr;
+    int ess_cap = 0;
     std::vector<void*> allocs;          // everything cudaMalloc'ed for the batch state
 
     // ---- pinned host staging ------------------------------------------------------------------
@@ -139,6 +143,9 @@ void vo_drop_graphs(vo_ctx* ctx);
 // new projection matrices: cached graphs carry the old calibration in their kernel arguments, so they are dropped
 void vo_set_calibration(vo_ctx* ctx, const float P_l[12], const float P_r[12]);
 int vo_drain_pending(vo_ctx* ctx);
+// Entry points that overwrite the shared image planes / unit-0 buffers call this first: refused (VO_E_INVALID) while
+// sequence frames or batch submissions are in flight; an idle sequence is ended (its planes are about to be reused).
+int vo_claim_buffers(vo_ctx* ctx, const char* who, bool allow_pending_batches = false);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);
 int vo_launch_bgr_to_gray(const uint8_t* d_bgr, size_t pitch, size_t img_stride_in, uint8_t* d_gray, size_t img_stride_out,
@@ -156,5 +163,5 @@ int vo_run_filter(vo_ctx* ctx, const View& v, bool with_ages);
 int vo_run_fast(vo_ctx* ctx, const View& v, int plane_in_unit, bool want_resp);
 int vo_run_select(vo_ctx* ctx, const View& v);
 // triangulate pts_l/pts_r ([units][cap], counts n) -> d_X ; PnP on (d_X, pts2d) -> d_results / d_inliers
-int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n);
+int vo_run_triangulate(vo_ctx* ctx, const View& v, const float2* pts_l, const float2* pts_r, const int* n, float4* X4 = nullptr);
 int vo_run_pnp(vo_ctx* ctx, const View& v, const float2* pts2d, const int* n, const float* K9);

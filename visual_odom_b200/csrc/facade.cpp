@@ -271,13 +271,23 @@ void triangulateStereo(cv::Mat& projMatrl, cv::Mat& projMatrr, std::vector<cv::P
 }
 
 void trackingFrame2Frame(cv::Mat& projMatrl, cv::Mat& /*projMatrr: unused by the reference too*/,
-                         std::vector<cv::Point2f>& /*pointsLeft_t0: only used by the mono branch*/,
+                         std::vector<cv::Point2f>& pointsLeft_t0,
                          std::vector<cv::Point2f>& pointsLeft_t1, cv::Mat& points3D_t0, cv::Mat& rotation,
                          cv::Mat& translation, bool mono_rotation)
 {
-    if (mono_rotation)
-        throw std::runtime_error("trackingFrame2Frame(mono_rotation=true): the 5-point essential-matrix branch is not built "
-                                 "(the reference's main() passes false, src/main.cpp:181)");
+    if (mono_rotation) {
+        // findEssentialMat(RANSAC, 0.999, 1.0) + recoverPose -> `rotation` (src/visualOdometry.cpp:146-157); the PnP below then
+        // only provides `translation` (the reference skips its cv::Rodrigues in this mode, :186-189)
+        if (pointsLeft_t0.size() != pointsLeft_t1.size()) throw std::runtime_error("trackingFrame2Frame: point count mismatch");
+        const double focal = projMatrl.at<float>(0, 0);
+        const double ppx = projMatrl.at<float>(0, 2), ppy = projMatrl.at<float>(1, 2);
+        double Rm[9];
+        check(vo_mono_rotation(context(), as_vo(pointsLeft_t0), as_vo(pointsLeft_t1), (int)pointsLeft_t0.size(), focal, ppx, ppy, Rm,
+                               nullptr, nullptr, nullptr), "vo_mono_rotation");
+        rotation = cv::Mat(3, 3, CV_64FC1);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) rotation.at<double>(r, c) = Rm[r * 3 + c];
+    }
     float K[9];
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) K[r * 3 + c] = projMatrl.at<float>(r, c);
@@ -292,9 +302,11 @@ void trackingFrame2Frame(cv::Mat& projMatrl, cv::Mat& /*projMatrr: unused by the
     check(vo_pnp_ransac(context(), reinterpret_cast<const vo_point3f*>(points3D_t0.data), as_vo(pointsLeft_t1), n, K, rvec, tvec,
                         inl.data(), &n_in, R, &iters), "vo_pnp_ransac");
     for (int k = 0; k < 3; k++) translation.at<double>(k) = tvec[k];
-    if (rotation.empty() || rotation.type() != CV_64FC1 || rotation.rows != 3 || rotation.cols != 3) rotation = cv::Mat(3, 3, CV_64FC1);
-    for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) rotation.at<double>(r, c) = R[r * 3 + c];
+    if (!mono_rotation) {                                           // `if (!mono_rotation) cv::Rodrigues(rvec, rotation);`
+        if (rotation.empty() || rotation.type() != CV_64FC1 || rotation.rows != 3 || rotation.cols != 3) rotation = cv::Mat(3, 3, CV_64FC1);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) rotation.at<double>(r, c) = R[r * 3 + c];
+    }
     g_last_inliers.assign(inl.begin(), inl.begin() + n_in);
     std::printf("[trackingFrame2Frame] inliers size: %d\n", n_in);
 }
@@ -314,15 +326,21 @@ void Frame::setFeatures(std::vector<cv::Point2f> l, std::vector<cv::Point2f> r)
 
 void Frame::triangulateFeaturePoints(cv::Mat& points4D)
 {
-    cv::Mat p3;
-    triangulateStereo(m_projMatL, m_projMatR, m_pointsFeatureLeft, m_pointsFeatureRight, p3);
-    const int n = p3.rows;
+    // cv::triangulatePoints(m_projMatL, m_projMatR, left, right, points4D): 4 x N CV_32F, unit-norm homogeneous columns
+    const int n = (int)m_pointsFeatureLeft.size();
+    if ((int)m_pointsFeatureRight.size() != n) throw std::runtime_error("Frame::triangulateFeaturePoints: left / right sizes differ");
     points4D = cv::Mat(4, n, CV_32FC1);
-    for (int i = 0; i < n; i++) {
-        const float* s = p3.ptr<float>(i);
-        points4D.at<float>(0, i) = s[0]; points4D.at<float>(1, i) = s[1]; points4D.at<float>(2, i) = s[2];
-        points4D.at<float>(3, i) = 1.f;
-    }
+    if (n == 0) return;
+    if (m_projMatL.type() != CV_32FC1 || m_projMatR.type() != CV_32FC1 || m_projMatL.rows != 3 || m_projMatL.cols != 4)
+        throw std::runtime_error("Frame::triangulateFeaturePoints: projection matrices must be 3x4 CV_32F");
+    float Pl[12], Pr[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) { Pl[r * 4 + c] = m_projMatL.at<float>(r, c); Pr[r * 4 + c] = m_projMatR.at<float>(r, c); }
+    std::vector<float> x4((size_t)n * 4);
+    check(vo_triangulate_homogeneous(context(), Pl, Pr, as_vo(m_pointsFeatureLeft), as_vo(m_pointsFeatureRight), n, x4.data()),
+          "vo_triangulate_homogeneous");
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 4; k++) points4D.at<float>(k, i) = x4[(size_t)i * 4 + k];
 }
 
 // ------------------------------------------------------------------------------------------------ utils.h

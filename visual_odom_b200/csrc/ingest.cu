@@ -388,6 +388,7 @@ extern "C" int vo_bgr_to_gray(vo_ctx* ctx, const uint8_t* bgr, size_t pitch, int
 {
     if (!ctx) return VO_E_INVALID;
     if (!bgr || !gray || w <= 0 || h <= 0 || pitch < (size_t)3 * w || gray_pitch < (size_t)w) { vo_set_error(ctx, "vo_bgr_to_gray: bad argument"); return VO_E_INVALID; }
+    { int rcc = vo_claim_buffers(ctx, "vo_bgr_to_gray"); if (rcc) return rcc; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     const size_t in_bytes = ((size_t)3 * w * h + 255) & ~(size_t)255;
     int rc = vo_ensure_bgr(ctx, in_bytes + (size_t)w * h);

@@ -258,9 +258,15 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
         __syncwarp();
     }
     uint32_t phase = 0;
+    // instantiations with 128 registers per thread keep the packed I patch and the packed residuals in registers;
+    // the others park them in the (then dead) window buffers
+    constexpr bool IN_REGS = CPS <= 8;
 
     const float half_win = (VO_WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
+    // delta.ddot(delta) <= eps^2 is a double test in OpenCV; dx*dx + dy*dy in float is within 2e-7 of it, so the double
+    // form is only evaluated inside this band
+    const float eps2_lo = (float)(args.eps2 * 0.999999), eps2_hi = (float)(args.eps2 * 1.000001);
     const int max_level = args.nlevels - 1;
     // Work items.  A feature-ring is ncalls x nlevels PHASES (one level-solve each).  An item is `span`
     // consecutive phases of one feature; items are queued phase-major, so every feature's phase p is handed out
@@ -349,9 +355,9 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
 
                 // ---- patch extraction: I (x32), Ix, Iy of the strip elements; A addends in chain order ----
                 int dxy[15];          // lo16 = Ix, hi16 = Iy
+                int Ipk[8];           // int16 patch intensities, two per register: strip 0..10, tail 11..14
                 float A11, A12, A22;
                 {
-                    int Ipk[8];           // int16 patch intensities, two per register: strip 0..10, tail 11..14
                     float a22v[15];       // A22 addends: their slots alias the derivative window, stored after the extraction
                     const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
                     const int ox = ipx + VO_PAD - ibx, odx = ipx + VO_PAD - dbx;
@@ -395,8 +401,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         const int k = e < 11 ? e : e - 11;
                         if (k < (e < 11 ? nvalid_s : tn)) a22[(e < 11 ? a_pos + k * 4 : t_pos + k * 5)] = a22v[e];
                     }
-                    ipk_s[lane] = make_uint4(Ipk[0], Ipk[1], Ipk[2], Ipk[3]);
-                    ipk_s[32 + lane] = make_uint4(Ipk[4], Ipk[5], Ipk[6], Ipk[7]);
+                    if (!IN_REGS) {
+                        ipk_s[lane] = make_uint4(Ipk[0], Ipk[1], Ipk[2], Ipk[3]);
+                        ipk_s[32 + lane] = make_uint4(Ipk[4], Ipk[5], Ipk[6], Ipk[7]);
+                    }
                     __syncwarp();
                     float acc = 0.f;
                     if (lane < 15) acc = run_chain<84>(run_slot, rc == 4);
@@ -449,10 +457,13 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
                     int sxs = 0, sys = 0, sxt = 0, syt = 0;         // signed sums: strip (my SIMD chain) / tail
                     unsigned axs = 0, ays = 0, axt = 0, ayt = 0;    // sums of |addend|
+                    int dpk[8];                       // int16 residuals, two per register (same element order as the I patch)
                     {
-                        int dpk[8];                   // int16 residuals, two per register (same element order as the I patch)
-                        const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
-                        const int Ipk[8] = {(int)i03.x, (int)i03.y, (int)i03.z, (int)i03.w, (int)i47.x, (int)i47.y, (int)i47.z, (int)i47.w};
+                        if (!IN_REGS) {
+                            const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
+                            Ipk[0] = (int)i03.x; Ipk[1] = (int)i03.y; Ipk[2] = (int)i03.z; Ipk[3] = (int)i03.w;
+                            Ipk[4] = (int)i47.x; Ipk[5] = (int)i47.y; Ipk[6] = (int)i47.z; Ipk[7] = (int)i47.w;
+                        }
 #pragma unroll
                         for (int part = 0; part < 2; part++) {
                             const int c0 = part ? tcol : col, row0 = part ? tr0 : r0, ne = part ? 4 : 11;
@@ -475,8 +486,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                                 ptop = pbot;
                             }
                         }
-                        dpk_s[lane] = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
-                        dpk_s[32 + lane] = make_uint4(dpk[4], dpk[5], dpk[6], dpk[7]);
+                        if (!IN_REGS) {
+                            dpk_s[lane] = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
+                            dpk_s[32 + lane] = make_uint4(dpk[4], dpk[5], dpk[6], dpk[7]);
+                        }
                     }
                     // per-chain totals (exact integers) and per-chain sums of |addend| (REDUX over the chain's lanes)
                     const unsigned cax = chain_sum_u(axs), cay = chain_sum_u(ays);
@@ -498,8 +511,11 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         ib1 = __shfl_sync(FULL, tot, 0); ib2 = __shfl_sync(FULL, tot, 1);
                     } else {
                         // faithful replay: float addends in chain order, runner lanes add them
-                        const uint4 d03 = dpk_s[lane], d47 = dpk_s[32 + lane];
-                        const int dpk[8] = {(int)d03.x, (int)d03.y, (int)d03.z, (int)d03.w, (int)d47.x, (int)d47.y, (int)d47.z, (int)d47.w};
+                        if (!IN_REGS) {
+                            const uint4 d03 = dpk_s[lane], d47 = dpk_s[32 + lane];
+                            dpk[0] = (int)d03.x; dpk[1] = (int)d03.y; dpk[2] = (int)d03.z; dpk[3] = (int)d03.w;
+                            dpk[4] = (int)d47.x; dpk[5] = (int)d47.y; dpk[6] = (int)d47.z; dpk[7] = (int)d47.w;
+                        }
 #pragma unroll
                         for (int k = 0; k < 11; k++) {
                             const int d = (k & 1) ? (dpk[k >> 1] >> 16) : (int)(short)(dpk[k >> 1] & 0xffff);
@@ -531,8 +547,13 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
                     npx = __fadd_rn(npx, dx); npy = __fadd_rn(npy, dy);
                     nxt.x = __fadd_rn(npx, half_win); nxt.y = __fadd_rn(npy, half_win);
-                    if ((double)dx * (double)dx + (double)dy * (double)dy <= args.eps2) break;
-                    if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                    {
+                        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                        if (d2 < eps2_lo) break;
+                        if (d2 <= eps2_hi && (double)dx * (double)dx + (double)dy * (double)dy <= args.eps2) break;
+                    }
+                    // std::abs(double(x)) < 0.01 for a float x  <=>  |x| <= 0.01f (0.01f is the largest float below 0.01)
+                    if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                         nxt.x = __fsub_rn(nxt.x, __fmul_rn(dx, 0.5f));
                         nxt.y = __fsub_rn(nxt.y, __fmul_rn(dy, 0.5f));
                         break;
@@ -569,8 +590,11 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         const unsigned wt = (unsigned)w00 | ((unsigned)w01 << 16), wb = (unsigned)w10 | ((unsigned)(w11 & 0xffff) << 16);
                         // errval += |diff| is a plain row-major float sum of small integers
                         // (<= 441 * 8160 < 2^24): exact, so any order gives the same float.
-                        const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
-                        const int Ipk[8] = {(int)i03.x, (int)i03.y, (int)i03.z, (int)i03.w, (int)i47.x, (int)i47.y, (int)i47.z, (int)i47.w};
+                        if (!IN_REGS) {
+                            const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
+                            Ipk[0] = (int)i03.x; Ipk[1] = (int)i03.y; Ipk[2] = (int)i03.z; Ipk[3] = (int)i03.w;
+                            Ipk[4] = (int)i47.x; Ipk[5] = (int)i47.y; Ipk[6] = (int)i47.z; Ipk[7] = (int)i47.w;
+                        }
                         int s = 0;
 #pragma unroll
                         for (int part = 0; part < 2; part++) {
@@ -636,25 +660,38 @@ static cudaError_t prep()
 cudaError_t vo_lk_prepare()
 {
     cudaError_t e;
-    if ((e = prep<true, LK_CTAS_PER_SM>()) != cudaSuccess) return e;
     if ((e = prep<false, LK_CTAS_PER_SM>()) != cudaSuccess) return e;
+    if ((e = prep<true, 12>()) != cudaSuccess) return e;
     if ((e = prep<true, 10>()) != cudaSuccess) return e;
+    if ((e = prep<true, 9>()) != cudaSuccess) return e;
     if ((e = prep<true, 8>()) != cudaSuccess) return e;
+    if ((e = prep<true, 7>()) != cudaSuccess) return e;
     return vo_lk_prepare_v3();
+}
+
+int vo_lk_ctas_per_sm(int requested)
+{
+    return (requested == 12 || requested == 10 || requested == 9 || requested == 8 || requested == 7) ? requested : LK_CTAS_PER_SM;
 }
 
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream)
 {
-    const long items = (long)args.n_units * args.per_unit;
+    const int nphases = args.ncalls * args.nlevels;
+    const int span = args.span > 0 && args.span < nphases ? args.span : nphases;
+    const long items = (long)args.n_units * args.per_unit;          // features; every feature has (nphases / span) work items
     if (items <= 0) return cudaSuccess;
     long ctas = (items + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA;
-    const int cps = (ctas_per_sm == 10 || ctas_per_sm == 8) && args.use_tma ? ctas_per_sm : LK_CTAS_PER_SM;
+    const int cps = args.use_tma ? vo_lk_ctas_per_sm(ctas_per_sm) : LK_CTAS_PER_SM;
     const long resident = (long)(sm_count > 0 ? sm_count : 148) * cps;
     if (ctas > resident) ctas = resident;
+    (void)span;
     const int thr = LK_WARPS_PER_CTA * 32;
-    if (!args.use_tma) k_lk_ring<false, LK_CTAS_PER_SM><<<(int)ctas, thr, vo_lk_smem_bytes(), stream>>>(maps, args);
-    else if (cps == 10) k_lk_ring<true, 10><<<(int)ctas, thr, vo_lk_smem_bytes(), stream>>>(maps, args);
-    else if (cps == 8) k_lk_ring<true, 8><<<(int)ctas, thr, vo_lk_smem_bytes(), stream>>>(maps, args);
-    else k_lk_ring<true, LK_CTAS_PER_SM><<<(int)ctas, thr, vo_lk_smem_bytes(), stream>>>(maps, args);
+    const size_t sh = vo_lk_smem_bytes();
+    if (!args.use_tma) k_lk_ring<false, LK_CTAS_PER_SM><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 12) k_lk_ring<true, 12><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 10) k_lk_ring<true, 10><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 9) k_lk_ring<true, 9><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 7) k_lk_ring<true, 7><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else k_lk_ring<true, 8><<<(int)ctas, thr, sh, stream>>>(maps, args);
     return cudaGetLastError();
 }

@@ -5,7 +5,7 @@
 // Resident warps per SM the kernel is built for: 12 persistent CTAs of 2 warps (<= 80 registers per thread,
 // 8960 B of shared memory per warp: 12 x (2 x 8960 + 1024 reserved) = 227 328 B of the SM's 233 472 B).
 #define LK_WARPS_PER_CTA 2
-#define LK_CTAS_PER_SM 12
+#define LK_CTAS_PER_SM 8
 
 struct LkMaps {
     CUtensorMap img_i[VO_MAX_LEVELS];  // u8 planes, box 48 x 22 x 1 (I window, 16-byte aligned start)
@@ -52,6 +52,7 @@ cudaError_t vo_lk_prepare();
 // ctas_per_sm: 0 = LK_CTAS_PER_SM; 10 / 8 select the instantiations built with more registers (A/B measurement)
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream);
 // round-1 kernel (one single-warp CTA per feature), kept for A/B measurement only
+int vo_lk_ctas_per_sm(int requested);     // the instantiation a request maps to
 cudaError_t vo_lk_prepare_v3();
 cudaError_t vo_launch_lk_ring_v3(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
 int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch, cudaStream_t stream);

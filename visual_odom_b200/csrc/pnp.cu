@@ -32,9 +32,10 @@ __global__ void k_triangulate(const TriArgs a)
     if (i >= n) return;
     const float2 pl = a.pts_l[(size_t)unit * a.cap + i];
     const float2 pr = a.pts_r[(size_t)unit * a.cap + i];
-    float o[3];
-    triangulate_dlt(a.Pl, a.Pr, pl.x, pl.y, pr.x, pr.y, o);
+    float o[3], o4[4];
+    triangulate_dlt(a.Pl, a.Pr, pl.x, pl.y, pr.x, pr.y, o, o4);
     a.X[(size_t)unit * a.cap + i] = make_float3(o[0], o[1], o[2]);
+    if (a.X4) a.X4[(size_t)unit * a.cap + i] = make_float4(o4[0], o4[1], o4[2], o4[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,18 +289,6 @@ __global__ void __launch_bounds__(128) k_pnp_count(const PnpArgs a, int it0, int
     if ((threadIdx.x & 31) == 0) atomicAdd(&total, c);
     __syncthreads();
     if (threadIdx.x == 0) a.counts[(size_t)unit * a.iterations + it] = total;
-}
-
-__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters)
-{
-    p = fmax(p, 0.); p = fmin(p, 1.);
-    ep = fmax(ep, 0.); ep = fmin(ep, 1.);
-    double num = fmax(1. - p, kDblMin);
-    double denom = 1. - pow(1. - ep, (double)model_points);
-    if (denom < kDblMin) return 0;
-    num = log(num);
-    denom = log(denom);
-    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
 }
 
 __global__ void k_pnp_replay(const PnpArgs a, int it0, int it1)

@@ -27,6 +27,7 @@ struct TriArgs {
     const float2* pts_l;     // [units][cap]
     const float2* pts_r;     // [units][cap]
     float3* X;               // [units][cap]
+    float4* X4;              // optional [units][cap]: homogeneous points as cv::triangulatePoints returns them
     double Pl[12], Pr[12];   // float projection matrices widened to double
 };
 

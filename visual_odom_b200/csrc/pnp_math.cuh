@@ -39,6 +39,19 @@ struct Rng {
     }
 };
 
+// cv::RANSACUpdateNumIters (ptsetreg.cpp)
+VO_HDN inline int ransac_update_num_iters(double p, double ep, int model_points, int max_iters)
+{
+    p = fmax(p, 0.); p = fmin(p, 1.);
+    ep = fmax(ep, 0.); ep = fmin(ep, 1.);
+    double num = fmax(1. - p, kDblMin);
+    double denom = 1. - pow(1. - ep, (double)model_points);
+    if (denom < kDblMin) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
 VO_HD double cv_hypot(double a, double b)
 {
     a = fabs(a); b = fabs(b);
@@ -673,8 +686,9 @@ VO_HDN inline void epnp5(const float* Xw_f, const float* uv_f, double fu, double
 
 // per-point DLT of cv::triangulatePoints: X4 = last row of V^T of the 4x4 system (stored float),
 // then convertPointsFromHomogeneous in float.
+// out4 (optional): the unit-norm homogeneous 4-vector itself, i.e. the column cv::triangulatePoints stores.
 VO_HDN inline void triangulate_dlt(const double* Pl, const double* Pr, float xl, float yl, float xr, float yr,
-                                   float* out3)
+                                   float* out3, float* out4 = nullptr)
 {
     double At[16], W[4], Vt[16];
     const double x = xl, y = yl, x2 = xr, y2 = yr;
@@ -687,6 +701,7 @@ VO_HDN inline void triangulate_dlt(const double* Pl, const double* Pr, float xl,
     }
     jacobi_svd_t<4, 4>(At, W, Vt, 4);
     const float X0 = (float)Vt[12], X1 = (float)Vt[13], X2 = (float)Vt[14], X3 = (float)Vt[15];
+    if (out4) { out4[0] = X0; out4[1] = X1; out4[2] = X2; out4[3] = X3; }
     const float scale = X3 != 0.f ? 1.f / X3 : 1.f;
     out3[0] = X0 * scale; out3[1] = X1 * scale; out3[2] = X2 * scale;
 }

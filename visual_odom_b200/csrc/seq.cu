@@ -18,6 +18,9 @@ __global__ void __launch_bounds__(1024) k_seq_append(const float2* __restrict__ 
                                                      int corner_cap, float2* feat_pts, int* feat_ages, int* cnt, int feat_cap,
                                                      int refill_below, int* err)
 {
+    // the error bits are per frame: this is the first glue kernel of a frame's front stage, it clears the frame's word
+    if (threadIdx.x == 0) *err = 0;
+    __syncthreads();
     const int n_pts = cnt[0], n_ages = cnt[1];
     if (n_pts >= refill_below) return;                 // `if (currentVOFeatures.size() < 2000)`
     int m = *n_det;
@@ -104,7 +107,7 @@ __global__ void k_seq_finish(vo_unit_result_dev* res, double* tprev_next, const 
     if (threadIdx.x == 0) {
         for (int k = 0; k < 3; k++) tprev_next[k] = res->tvec[k];
         res->n_features = *n_feat; res->n_detected = *n_det; res->n_tracked = *n3; res->n_valid = *n5;
-        *err_out = *err;
+        if (err_out != err) *err_out = *err;
     }
 }
 

@@ -59,7 +59,7 @@ static void seq_args(vo_ctx* ctx, int unit, SeqArgs& a)
     a.valid_l1 = ctx->d_valid4 + 2 * cs + uo; a.n5 = ctx->d_n5 + unit; a.ages_out = ctx->d_ages_out + uo; a.n3 = ctx->d_n3 + unit;
     a.res = ctx->d_results + unit;
     a.tprev = ctx->d_tprev + 3 * (size_t)(1 - unit);          // the next frame solves from this frame's translation
-    a.err = ctx->d_seq_err; a.err_out = ctx->d_seq_err + 1 + unit;
+    a.err = ctx->d_seq_err + 1 + unit; a.err_out = ctx->d_seq_err + 1 + unit;      // one word per buffer unit = per frame in flight
 }
 
 // front stage of one frame on the caller's stream; s0 / s1 = image slots of the previous / new pair, unit = per-frame buffers
@@ -271,7 +271,9 @@ extern "C" int vo_seq_wait(vo_ctx* ctx, vo_unit_result* out, vo_point2f* pts4, i
     memcpy(out, &rec.r, sizeof(rec.r));
     ctx->seq_inflight--;
     ctx->seq_frames++;
-    if (rec.r.pnp_status == VO_OK) vo_pose_step(ctx->seq_pose, rec.r.R, rec.r.tvec);   // main.cpp:196-208
+    // main.cpp:196-208.  The reference ignores solvePnPRansac's return value: when RANSAC finds no model, rvec stays 0
+    // (R = I) and `translation` keeps the carried value, and the main loop still integrates that motion.
+    if (rec.r.pnp_status == VO_OK || rec.r.pnp_status == VO_PNP_NO_MODEL) vo_pose_step(ctx->seq_pose, rec.r.R, rec.r.tvec);
     if (pts4 && pts_cap > 0 && rec.r.n_valid > 0) {
         // the frame's point lists stay in its buffer unit until the frame after next is submitted
         const size_t cs = (size_t)ctx->units * ctx->cap, uo = (size_t)unit * ctx->cap;
@@ -281,7 +283,8 @@ extern "C" int vo_seq_wait(vo_ctx* ctx, vo_unit_result* out, vo_point2f* pts4, i
             VO_CUDA_CHECK(cudaMemcpyAsync(pts4 + (size_t)k * pts_cap, ctx->d_valid4 + k * cs + uo, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, sb));
         VO_CUDA_CHECK(cudaStreamSynchronize(sb));
     }
-    if (rec.err) { vo_set_error(ctx, "vo_seq: glue kernel error bits 0x%x (1/2: capacity, 4: bucket grid, 8: feature outside the image)", rec.err); return VO_E_CAPACITY; }
+    // bit 8 (a tracked point outside the bucket grid: undefined behaviour in the reference, dropped here) is not an error
+    if (rec.err & ~8) { vo_set_error(ctx, "vo_seq: glue kernel error bits 0x%x of this frame (1/2: capacity, 4: bucket grid)", rec.err); return VO_E_CAPACITY; }
     return VO_OK;
 }
 

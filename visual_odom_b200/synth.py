@@ -122,3 +122,20 @@ def pnp_stress_set(n=1500, sigma=0.15, outlier_frac=0.3, seed=0, cal=KITTI00, rv
     out = rng.random(n) < outlier_frac
     x[out] += rng.uniform(-15, 15, (int(out.sum()), 2))
     return X, x.astype(np.float32), P_l[:, :3].copy(), out
+
+
+def essential_stress_set(n, sigma, outlier_frac, seed, cal=KITTI00, rvec=EGO_RVEC, tvec=EGO_T):
+    """Image points of n world points before / after the ego-motion (pixel noise sigma on both, a fraction of gross
+    outliers in the second view) + the (focal, principal point) the reference's mono branch reads from P_l as floats
+    (reference src/visualOdometry.cpp:144-145).  Returns (p_t0, p_t1, focal, pp)."""
+    rng = np.random.default_rng(seed)
+    P_l, _ = proj_matrices(cal)
+    K = P_l[:, :3].astype(np.float64)
+    X = np.stack([rng.uniform(-30, 30, n), rng.uniform(-3, 6, n), rng.uniform(6, 80, n)], 1)
+    x0 = np.stack([X[:, 0] / X[:, 2] * K[0, 0] + K[0, 2], X[:, 1] / X[:, 2] * K[1, 1] + K[1, 2]], 1)
+    Xc = X @ _rodrigues(rvec).T + np.asarray(tvec, np.float64)
+    x1 = np.stack([Xc[:, 0] / Xc[:, 2] * K[0, 0] + K[0, 2], Xc[:, 1] / Xc[:, 2] * K[1, 1] + K[1, 2]], 1)
+    x0 += rng.normal(0, sigma, x0.shape); x1 += rng.normal(0, sigma, x1.shape)
+    o = rng.random(n) < outlier_frac
+    x1[o] += rng.uniform(-15, 15, (int(o.sum()), 2))
+    return x0.astype(np.float32), x1.astype(np.float32), float(np.float32(K[0, 0])), (float(np.float32(K[0, 2])), float(np.float32(K[1, 2])))
