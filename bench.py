@@ -524,8 +524,7 @@ class Point:
             if self.full_outputs:                              # what matchingFeatures / trackingFrame2Frame hand back
                 self.last_outputs = [ctx.batch_outputs(slot + u, out[u], into=self.into[s & 1][u]) for u in range(B)]
             if self.gather is not None:                        # result gather: fixed-size records over NCCL, non-blocking
-                from visual_odom_b200 import dist as vd
-                self.gather.post([vd.result_to_record(r) for r in out], self.my_units)
+                self.gather.post_step(slot, out, self.my_units)
         if self.gather is not None:
             self.tables = self.gather.drain()                  # the last tables arrive inside the timed region
         if ev:
@@ -544,6 +543,46 @@ class Point:
         if full_outputs and self.last_outputs:
             self.d2h_outputs = self.B * self.last_outputs[0]["d2h_bytes"]
         return ms, walls, res
+
+
+class NativeGather:
+    """Record gather through the library's own C-ABI (vo_dist_*: ncclAllGather straight from the device records of the
+    waited submission, one D2H into pinned memory, nothing blocks until two gathers are outstanding)."""
+    kind = "C-ABI vo_dist_gather_post / vo_dist_gather_wait (NCCL resolved with dlopen inside libvo_b200.so)"
+
+    def __init__(self, ctx, B):
+        self.ctx, self.B, self.outstanding, self.tables = ctx, B, 0, []
+
+    def _harvest(self):
+        self.tables.append(self.ctx.dist_gather_wait(self.B))
+        self.outstanding -= 1
+
+    def post_step(self, slot, out, my_units):
+        if self.outstanding == 2:
+            self._harvest()
+        self.ctx.dist_gather_post(slot, self.B)
+        self.outstanding += 1
+
+    def drain(self):
+        while self.outstanding:
+            self._harvest()
+        out, self.tables = self.tables, []
+        return out
+
+
+class TorchGather:
+    """Fallback when the host has no loadable NCCL for the C-ABI path: torch.distributed all_gather on a side stream."""
+    kind = "torch.distributed all_gather_into_tensor on a side stream (visual_odom_b200/dist.py AsyncRecordGather)"
+
+    def __init__(self, n_units):
+        from visual_odom_b200 import dist as vd
+        self.vd, self.g = vd, vd.AsyncRecordGather(n_units, device="cuda")
+
+    def post_step(self, slot, out, my_units):
+        self.g.post([self.vd.result_to_record(r) for r in out], my_units)
+
+    def drain(self):
+        return self.g.drain()
 
 
 def lk_profile_constants():
@@ -606,7 +645,7 @@ def main():
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    for opt in ("graphs", "priorities", "batch_graphs", "lk_span", "lk_ctas_per_sm", "lk_kernel"):   # A/B switches, e.g. VO_OPT_LK_SPAN=16
+    for opt in ("graphs", "priorities", "batch_graphs", "lk_span", "lk_ctas_per_sm", "lk_kernel", "lk_quota"):   # A/B switches, e.g. VO_OPT_LK_SPAN=16
         if os.environ.get("VO_OPT_" + opt.upper()) is not None:
             ctx.set_option(opt, float(os.environ["VO_OPT_" + opt.upper()]))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -616,7 +655,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather = vd.AsyncRecordGather(world * B, device="cuda") if world > 1 else None
+    gather = None
+    if world > 1:
+        try:                               # NCCL unique id: made by rank 0 inside the library, broadcast out of band
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.from_numpy(ctx.dist_unique_id()))
+            dist.broadcast(uid, src=0)
+            ctx.dist_init(uid.cpu().numpy(), rank, world)
+            gather = NativeGather(ctx, B)
+        except Exception as e:
+            if rank == 0:
+                print(f"bench: C-ABI gather unavailable ({str(e)[:120]}), using torch.distributed", file=sys.stderr)
+            gather = TorchGather(world * B)
     P = units[0]
     pt = Point(ctx, torch, stream, flush, pinned, args.features, B, W_IMG, H_IMG, P["P_l"], P["P_r"], barrier, world, gather, my_units)
     BLOCKS = 5                            # the K-step timed region is repeated and the median block reported (a block is ~40 ms)
@@ -633,7 +684,16 @@ def main():
     ref = reference_unit_outputs(units[last_slot_unit], args.features)
     bad = check_against_oracle(pt.last_outputs[last_slot_unit], res_e2e[last_slot_unit], ref)
     oracle_s = time.perf_counter() - t_or
-    ok_t = torch.tensor([0.0 if bad else 1.0], dtype=torch.float64, device="cuda")
+    gather_ok = True
+    if world > 1 and getattr(pt, "tables", None):          # the gathered table holds this rank's records where they belong
+        last = pt.tables[-1]
+        if isinstance(gather, NativeGather):
+            mine = last[rank * B:(rank + 1) * B]
+            gather_ok = len(last) == world * B and all(a["n_inliers"] == b["n_inliers"] and np.array_equal(a["tvec"], b["tvec"])
+                                                       for a, b in zip(mine, res_e2e))
+        else:
+            gather_ok = all(int(last[u][4]) == res_e2e[i]["n_inliers"] for i, u in enumerate(my_units))
+    ok_t = torch.tensor([0.0 if (bad or not gather_ok) else 1.0], dtype=torch.float64, device="cuda")
 
     # max over ranks (device-timed), block by block
     tt = torch.tensor(ms_res + ms_e2e + ms_sum + [lk_ms, float(feats_per_launch)], dtype=torch.float64, device="cuda")
@@ -709,7 +769,7 @@ def main():
                             "(4 images per unit from pinned host memory), kernels, and D2H of the result records AND of every unit's point "
                             "lists (4 x n_valid points, tracked-feature indices, points3D, inlier list: one packed copy per submission) "
                             "are inside the timed region" + ("; the NCCL all-gather of the records runs non-blocking on a side stream and "
-                                                             "is drained inside the timed region" if world > 1 else ""),
+                                                             "is drained inside the timed region (" + gather.kind + ")" if world > 1 else ""),
                     "summary_only": {"value": frames / (ms_sum * 1e-3), "d2h_bytes_per_step": d2h_records,
                                      "note": "round-1 definition: result records only"},
                     "equals_resident_results": all(a["n_inliers"] == b["n_inliers"] and np.array_equal(a["tvec"], b["tvec"])
@@ -729,7 +789,7 @@ def main():
                                  "issue_frac / warp_inst_per_feature_ring come from the committed ncu capture named in profile_source"},
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "parity": {"vs_oracle": parity_ok, "units_checked": world, "mismatches_rank0": bad,
+            "parity": {"vs_oracle": parity_ok, "units_checked": world, "mismatches_rank0": bad, "gathered_records_ok_rank0": gather_ok,
                        "oracle": "cv2 4.13.0 through oracle/ref_path.py (the reference's glue), one unit per rank, outside the timed region",
                        "oracle_seconds_rank0": oracle_s,
                        "n_valid": [r["n_valid"] for r in res], "n_inliers": [r["n_inliers"] for r in res]},

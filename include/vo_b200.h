@@ -203,6 +203,18 @@ VO_API int vo_batch_outputs(vo_ctx* ctx, int unit, vo_point2f* pts4, int32_t* ke
 VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f* pts4, int32_t* kept_idx,
                           vo_point3f* X, int32_t* inliers);
 
+/* ---- multi-GPU: gather of the result records over NCCL (one process per GPU, units sharded) -----------
+ * The path has no data-path collective; the only exchange is the gather of the fixed-size records.  NCCL is resolved with
+ * dlopen at vo_dist_init (VO_E_UNSUPPORTED when the host has none).  Rank 0 makes the id with vo_dist_unique_id and hands the
+ * 128 bytes to the other ranks out of band; every rank calls vo_dist_init once.  vo_dist_gather_post enqueues, without
+ * blocking, an ncclAllGather of the records of resident slots [first_unit, first_unit + n_units) (same n_units on every
+ * rank) straight from device memory plus one copy into pinned staging; at most two posts may be outstanding.
+ * vo_dist_gather_wait returns the oldest one: all[r * n_units + i] = record i of rank r. */
+VO_API int vo_dist_unique_id(uint8_t id_out[128]);
+VO_API int vo_dist_init(vo_ctx* ctx, const uint8_t id[128], int rank, int world);
+VO_API int vo_dist_gather_post(vo_ctx* ctx, int first_unit, int n_units);
+VO_API int vo_dist_gather_wait(vo_ctx* ctx, vo_unit_result* all, int cap_records, int* n_records);
+
 /* ---- streaming sequence mode ------------------------------------------------
  * The state of the reference's main loop (src/main.cpp:87-92,123-181: currentVOFeatures, the previous
  * stereo pair, `translation`) lives on the device.  vo_seq_begin uploads the first pair; each vo_seq_push

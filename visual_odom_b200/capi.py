@@ -102,6 +102,10 @@ SIGNATURES = {
     "vo_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vo_mono_rotation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                    C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vo_dist_unique_id": (C.c_int, [C.c_void_p]),
+    "vo_dist_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "vo_dist_gather_post": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vo_dist_gather_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vo_batch_outputs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
 }
 
@@ -377,6 +381,29 @@ class Context:
         flat = into["pts4"].reshape(-1, 2)            # the C side packs the four lists back to back (n_valid each)
         return dict(l0=flat[0:nv], r0=flat[nv:2 * nv], l1=flat[2 * nv:3 * nv], r1=flat[3 * nv:4 * nv], kept_idx=into["kept_idx"][:nv],
                     X=into["X"][:nv], inliers=into["inliers"][:ni], d2h_bytes=int(nb.value))
+
+    # ---- multi-GPU record gather over NCCL (one process per GPU) -------------------------------------
+    def dist_unique_id(self):
+        buf = np.zeros(128, np.uint8)
+        rc = self.lib.vo_dist_unique_id(_p(buf))
+        if rc != VO_OK:
+            raise VoError(rc, "vo_dist_unique_id: NCCL is not available on this host")
+        return buf
+
+    def dist_init(self, uid, rank, world):
+        uid = np.ascontiguousarray(uid, np.uint8)
+        assert uid.size == 128
+        self._check(self.lib.vo_dist_init(self.h, _p(uid), int(rank), int(world)))
+        self._dist_world = int(world)
+
+    def dist_gather_post(self, first_unit, n_units):
+        self._check(self.lib.vo_dist_gather_post(self.h, int(first_unit), int(n_units)))
+
+    def dist_gather_wait(self, n_units):
+        res = (VoUnitResult * (self._dist_world * n_units))()
+        n = C.c_int(0)
+        self._check(self.lib.vo_dist_gather_wait(self.h, res, len(res), C.byref(n)))
+        return [self._result_dict(r) for r in res[:n.value]]
 
     # ---- streaming sequence mode -------------------------------------------------------------------
     def seq_begin(self, left0, right0, P_l, P_r):

@@ -241,7 +241,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
     if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
-        if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma && g.s == v.s) {
+        if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma && g.s == v.s && g.max_pts == ctx->batch_max_pts) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));
             ctx->launches += g.launches;
             return VO_OK;
@@ -257,7 +257,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     VO_CUDA_CHECK(e);
     vo_ctx::RangeGraph g;
-    g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma; g.s = v.s;
+    g.u0 = v.u0; g.n = v.n; g.detect = ctx->batch_detect; g.tma = ctx->lk_use_tma; g.s = v.s; g.max_pts = ctx->batch_max_pts;      // the LK launch geometry depends on max_pts
     g.launches = ctx->launches - before;
     VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
@@ -391,6 +391,7 @@ extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit
     cudaStream_t st = ctx->side_stream[c];
     VO_CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
     VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+    if ((rc = vo_dist_order_after_gathers(ctx, st))) return rc;
     ctx->batch_detect = detect;
     if (max_pts > ctx->batch_max_pts || units) ctx->batch_max_pts = max_pts;
     if (units) {

@@ -80,6 +80,7 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     cudaSetDevice(ctx->device);
     vo_drain_pending(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    vo_dist_shutdown(ctx);
     vo_free_state(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& p : ctx->pending) if (p.done) cudaEventDestroy(p.done);
@@ -127,6 +128,7 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
     if (strcmp(key, "lk_ctas_per_sm") == 0) { ctx->lk_ctas_per_sm = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "batch_outputs") == 0) { ctx->batch_outputs = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
+    if (strcmp(key, "lk_quota") == 0) { ctx->lk_quota = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_span") == 0) { ctx->lk_span = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_kernel") == 0) { ctx->lk_kernel = value == 3 ? 3 : 4; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
@@ -451,7 +453,9 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         a.progress = ctx->d_lk_progress + uo;
         {   // a launch with fewer features than resident warps gains nothing from splitting its rings
             const long resident_warps = (long)ctx->sm_count * vo_lk_ctas_per_sm(ctx->lk_ctas_per_sm) * LK_WARPS_PER_CTA;
-            a.span = ctx->lk_span > 0 ? ctx->lk_span : ((long)a.n_units * a.per_unit > resident_warps ? 1 : 0);
+            const bool big = (long)a.n_units * a.per_unit > resident_warps;
+            a.span = ctx->lk_span > 0 ? ctx->lk_span : (big ? 2 : 0);
+            a.quota = big ? ctx->lk_quota : 0;
         }
         VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->sm_count, ctx->lk_ctas_per_sm, v.s));
     }

@@ -82,6 +82,17 @@ struct vo_ctx {
     double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
     uint8_t* d_bgr = nullptr;           // staging of colour (BGR) inputs, converted by k_bgr_to_gray (ingest.cu)
     size_t bgr_bytes = 0;
+    // multi-GPU record gather over NCCL (dist.cu); NCCL is dlopen'ed at vo_dist_init
+    void* dist_comm = nullptr;
+    int dist_rank = 0, dist_world = 1;
+    cudaStream_t dist_stream = nullptr;
+    cudaEvent_t dist_ev_read[2] = {nullptr, nullptr}, dist_ev_done[2] = {nullptr, nullptr}, dist_ev_fork = nullptr;
+    void* d_dist[2] = {nullptr, nullptr};
+    void* h_dist[2] = {nullptr, nullptr};
+    size_t dist_bytes = 0;
+    bool dist_posted[2] = {false, false};
+    int dist_n[2] = {0, 0};
+    long long dist_head = 0, dist_tail = 0;
     // mono_rotation branch (ess.cu): scratch of the essential-matrix RANSAC, allocated on first use
     void* d_ess = nullptr;
     int ess_cap = 0;
@@ -99,6 +110,8 @@ struct vo_ctx {
     bool lk_timing = true;
     bool lk_use_tma = true;
     int lk_ctas_per_sm = 0;             // 0 = the default instantiation (LK_CTAS_PER_SM)
+    int lk_quota = 0;                   // work items a warp takes before its CTA retires (0 = persistent): retiring CTAs let the
+                                        // high-priority helper kernels of the other unit range onto the SMs between LK work
     int lk_span = 0;                    // phases per LK work item: 0 = automatic (one level-solve per item when a launch has
                                         // more features than resident warps, else one item per feature-ring)
     int* d_lk_progress = nullptr;       // [units][cap] hand-over counters of the LK work items (zero between launches)
@@ -115,7 +128,7 @@ struct vo_ctx {
     bool batch_detect = false;      // features come from the on-GPU FAST + stride selection
     int batch_streams = 2;          // unit ranges run concurrently by the batched path
     bool use_graphs = true;         // replay the per-range kernel sequence as a CUDA graph (no LK event timing then)
-    struct RangeGraph { int u0, n; bool detect, tma; cudaStream_t s; cudaGraphExec_t exec; long long launches; };   // s: the stream it was captured on (its LK work queue is that stream's)
+    struct RangeGraph { int u0, n; bool detect, tma; cudaStream_t s; int max_pts; cudaGraphExec_t exec; long long launches; };   // s: the stream it was captured on (its LK work queue is that stream's)
     std::vector<RangeGraph> graphs; // invalidated when the device state is re-allocated
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
     cudaStream_t hi_stream[2] = {nullptr, nullptr};     // high-priority helpers of the side streams (see run_range_launch)
@@ -145,6 +158,8 @@ void vo_set_calibration(vo_ctx* ctx, const float P_l[12], const float P_r[12]);
 int vo_drain_pending(vo_ctx* ctx);
 // Entry points that overwrite the shared image planes / unit-0 buffers call this first: refused (VO_E_INVALID) while
 // sequence frames or batch submissions are in flight; an idle sequence is ended (its planes are about to be reused).
+int vo_dist_order_after_gathers(vo_ctx* ctx, cudaStream_t st);
+void vo_dist_shutdown(vo_ctx* ctx);
 int vo_claim_buffers(vo_ctx* ctx, const char* who, bool allow_pending_batches = false);
 int vo_ensure_pinned(vo_ctx* ctx, size_t bytes);
 int vo_ensure_bgr(vo_ctx* ctx, size_t bytes);

@@ -37,12 +37,25 @@ __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* const* __rest
         const int v = p[0];
         int d[16];
         unsigned hi = 0, lo = 0;
+        // quick reject on the four compass pixels: an arc of 9 contiguous ring pixels holds at least two of them
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < 16; k += 4) {
             const int r = p[c_ring_dy[k] * pitch + c_ring_dx[k]];
             d[k] = v - r;
             hi |= (unsigned)(r > v + threshold) << k;
             lo |= (unsigned)(r < v - threshold) << k;
+        }
+        if (__popc(hi) >= 2 || __popc(lo) >= 2) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if ((k & 3) == 0) continue;
+                const int r = p[c_ring_dy[k] * pitch + c_ring_dx[k]];
+                d[k] = v - r;
+                hi |= (unsigned)(r > v + threshold) << k;
+                lo |= (unsigned)(r < v - threshold) << k;
+            }
+        } else {
+            hi = lo = 0;
         }
         // >= 9 contiguous set bits on the 16-cycle
         unsigned mh = hi | (hi << 16), ml = lo | (lo << 16);

@@ -280,7 +280,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
     const int per_group = args.n_units * args.per_unit;
     const int items = ((nphases + span - 1) / span) * per_group;
 
-    for (;;) {
+    for (int taken = 0; args.quota <= 0 || taken < args.quota; taken++) {
         int item = 0;
         if (lane == 0) item = atomicAdd(args.queue, 1);
         item = __shfl_sync(FULL, item, 0);
@@ -637,7 +637,8 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
         }
     } // work queue
 
-    // the last warp to run dry resets the queue for the next launch that uses it
+    // the last warp to retire resets the queue for the next launch that uses it (every warp of the grid passes here once,
+    // after its last fetch)
     if (lane == 0) {
         const int total_warps = gridDim.x * LK_WARPS_PER_CTA;
         if (atomicAdd(args.queue + 1, 1) == total_warps - 1) {
@@ -666,12 +667,14 @@ cudaError_t vo_lk_prepare()
     if ((e = prep<true, 9>()) != cudaSuccess) return e;
     if ((e = prep<true, 8>()) != cudaSuccess) return e;
     if ((e = prep<true, 7>()) != cudaSuccess) return e;
+    if ((e = prep<true, 6>()) != cudaSuccess) return e;
+    if ((e = prep<true, 5>()) != cudaSuccess) return e;
     return vo_lk_prepare_v3();
 }
 
 int vo_lk_ctas_per_sm(int requested)
 {
-    return (requested == 12 || requested == 10 || requested == 9 || requested == 8 || requested == 7) ? requested : LK_CTAS_PER_SM;
+    return (requested == 12 || requested == 10 || (requested >= 5 && requested <= 9)) ? requested : LK_CTAS_PER_SM;
 }
 
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream)
@@ -680,11 +683,16 @@ cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_cou
     const int span = args.span > 0 && args.span < nphases ? args.span : nphases;
     const long items = (long)args.n_units * args.per_unit;          // features; every feature has (nphases / span) work items
     if (items <= 0) return cudaSuccess;
-    long ctas = (items + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA;
     const int cps = args.use_tma ? vo_lk_ctas_per_sm(ctas_per_sm) : LK_CTAS_PER_SM;
     const long resident = (long)(sm_count > 0 ? sm_count : 148) * cps;
-    if (ctas > resident) ctas = resident;
-    (void)span;
+    long ctas;
+    if (args.quota > 0) {           // every warp takes `quota` items: enough CTAs for all of them (they queue for SM slots)
+        const long work_items = ((nphases + span - 1) / span) * items;
+        ctas = (work_items + (long)args.quota * LK_WARPS_PER_CTA - 1) / ((long)args.quota * LK_WARPS_PER_CTA);
+    } else {
+        ctas = (items + LK_WARPS_PER_CTA - 1) / LK_WARPS_PER_CTA;
+        if (ctas > resident) ctas = resident;
+    }
     const int thr = LK_WARPS_PER_CTA * 32;
     const size_t sh = vo_lk_smem_bytes();
     if (!args.use_tma) k_lk_ring<false, LK_CTAS_PER_SM><<<(int)ctas, thr, sh, stream>>>(maps, args);
@@ -692,6 +700,8 @@ cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_cou
     else if (cps == 10) k_lk_ring<true, 10><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else if (cps == 9) k_lk_ring<true, 9><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else if (cps == 7) k_lk_ring<true, 7><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 6) k_lk_ring<true, 6><<<(int)ctas, thr, sh, stream>>>(maps, args);
+    else if (cps == 5) k_lk_ring<true, 5><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else k_lk_ring<true, 8><<<(int)ctas, thr, sh, stream>>>(maps, args);
     return cudaGetLastError();
 }

@@ -37,6 +37,7 @@ struct LkArgs {
     int* queue;
     int per_unit;           // feature slots per unit that can be live (<= cap)
     int span;               // phases (level-solves) per work item; 0 or >= ncalls*nlevels = one item per feature-ring
+    int quota;              // work items a warp takes before it retires (0 = until the queue is empty)
     int* progress;          // [n_units][cap] phases completed per feature (hand-over between items; all zero between launches)
     // plain-load staging (debug / A-B measurement; VO_LK_STAGING=ldg): plane geometry per level
     int use_tma;

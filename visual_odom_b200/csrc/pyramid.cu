@@ -14,6 +14,8 @@
 // 64-byte aligned (pitch % 64 == 0).  No tensor cores (no contraction here).
 #include "common.cuh"
 
+static __device__ __forceinline__ uint32_t ldw(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+
 // ---------------------------------------------------------------------------------------------
 // raw (pitch = src_pitch) -> padded level 0.  grid.z = image index.
 // src images are addressed through a pointer table (one entry per image).
@@ -50,29 +52,41 @@ __global__ void k_pyr_level(LevelGeom s, LevelGeom d, int has_next)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = blockIdx.y;
 
-    // (a) derivative of level s: rows [0,h), 4 pixels per thread
+    // (a) derivative of level s: rows [0,h), 4 pixels per thread.  The six bytes x0-1 .. x0+4 of a row come from three
+    // aligned words (x0 and the row base are multiples of 4; the padding keeps x0-4 and x0+7 inside the plane).
     if (row < s.h) {
         const int x0 = 4 * q;
         if (x0 < s.w) {
             uint32_t* __restrict__ dp = s.der + (size_t)img * s.plane + (size_t)(row + VO_PAD) * s.pitch + VO_PAD;
-            const uint8_t* r0 = sp + (size_t)(row - 1) * s.pitch;
-            const uint8_t* r1 = sp + (size_t)row * s.pitch;
-            const uint8_t* r2 = sp + (size_t)(row + 1) * s.pitch;
             int t0[6], t1[6];
+            {
+                int b[3][6];
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                int x = x0 - 1 + i;
-                int a = r0[x], b = r1[x], c = r2[x];
-                t0[i] = (a + c) * 3 + b * 10;
-                t1[i] = c - a;
+                for (int k = 0; k < 3; k++) {
+                    const uint8_t* r = sp + (size_t)(row - 1 + k) * s.pitch + x0;
+                    const uint32_t w0 = ldw(r - 4), w1 = ldw(r), w2 = ldw(r + 4);
+                    b[k][0] = w0 >> 24; b[k][1] = w1 & 255; b[k][2] = (w1 >> 8) & 255; b[k][3] = (w1 >> 16) & 255;
+                    b[k][4] = w1 >> 24; b[k][5] = w2 & 255;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    t0[i] = (b[0][i] + b[2][i]) * 3 + b[1][i] * 10;
+                    t1[i] = b[2][i] - b[0][i];
+                }
             }
+            uint32_t o[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (x0 + i < s.w) {
-                    int dx = t0[i + 2] - t0[i];
-                    int dy = (t1[i] + t1[i + 2]) * 3 + t1[i + 1] * 10;
-                    dp[x0 + i] = ((uint32_t)(uint16_t)(int16_t)dx) | ((uint32_t)(uint16_t)(int16_t)dy << 16);
-                }
+                const int dx = t0[i + 2] - t0[i];
+                const int dy = (t1[i] + t1[i + 2]) * 3 + t1[i + 1] * 10;
+                o[i] = ((uint32_t)(uint16_t)(int16_t)dx) | ((uint32_t)(uint16_t)(int16_t)dy << 16);
+            }
+            if (x0 + 3 < s.w) {
+                *reinterpret_cast<uint4*>(dp + x0) = make_uint4(o[0], o[1], o[2], o[3]);     // (PAD + x0) elements = 16-byte aligned
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (x0 + i < s.w) dp[x0 + i] = o[i];
             }
         }
     }
@@ -84,20 +98,42 @@ __global__ void k_pyr_level(LevelGeom s, LevelGeom d, int has_next)
             uint8_t* __restrict__ dst = d.img + (size_t)img * d.plane + (size_t)row * d.pitch;
             const int dy = vo_reflect101(row - VO_PAD, d.h);
             uint32_t out = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int dx = vo_reflect101(4 * q + i - VO_PAD, d.w);
-                // source taps 2*dx-2..2*dx+2 lie inside [-2, w+1]: the REFLECT_101 border of level s
-                const uint8_t* c = sp + (size_t)(2 * dy - 2) * s.pitch + (2 * dx - 2);
-                int acc = 0;
+            const int dx0 = 4 * q - VO_PAD;
+            if (dx0 >= 0 && dx0 + 3 < d.w) {
+                // interior group: the 11 source bytes 2 dx0 - 2 .. 2 dx0 + 8 of a row come from four aligned words
+                int acc[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    const uint8_t* r = c + (size_t)j * s.pitch;
-                    int h = r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2];
+                    const uint8_t* r = sp + (size_t)(2 * dy - 2 + j) * s.pitch + 2 * dx0;
+                    const uint32_t w0 = ldw(r - 4), w1 = ldw(r), w2 = ldw(r + 4), w3 = ldw(r + 8);
+                    int v[11];                                   // v[k] = source pixel 2 dx0 - 2 + k
+                    v[0] = (w0 >> 16) & 255; v[1] = w0 >> 24;
+                    v[2] = w1 & 255; v[3] = (w1 >> 8) & 255; v[4] = (w1 >> 16) & 255; v[5] = w1 >> 24;
+                    v[6] = w2 & 255; v[7] = (w2 >> 8) & 255; v[8] = (w2 >> 16) & 255; v[9] = w2 >> 24;
+                    v[10] = w3 & 255;
                     const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
-                    acc += kj * h;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        acc[i] += kj * (v[2 * i] + v[2 * i + 4] + 4 * (v[2 * i + 1] + v[2 * i + 3]) + 6 * v[2 * i + 2]);
                 }
-                out |= (uint32_t)((acc + 128) >> 8) << (8 * i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) out |= (uint32_t)((acc[i] + 128) >> 8) << (8 * i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int dx = vo_reflect101(4 * q + i - VO_PAD, d.w);
+                    // source taps 2*dx-2..2*dx+2 lie inside [-2, w+1]: the REFLECT_101 border of level s
+                    const uint8_t* c = sp + (size_t)(2 * dy - 2) * s.pitch + (2 * dx - 2);
+                    int acc = 0;
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const uint8_t* r = c + (size_t)j * s.pitch;
+                        int h = r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2];
+                        const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+                        acc += kj * h;
+                    }
+                    out |= (uint32_t)((acc + 128) >> 8) << (8 * i);
+                }
             }
             *reinterpret_cast<uint32_t*>(dst + 4 * q) = out;
         }

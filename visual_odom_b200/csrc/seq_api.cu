@@ -133,7 +133,7 @@ static int seq_graph(vo_ctx* ctx, int key, cudaStream_t st, F launch)
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     VO_CUDA_CHECK(e);
     vo_ctx::RangeGraph g;
-    g.u0 = key; g.n = 1; g.detect = true; g.tma = ctx->lk_use_tma; g.s = st;
+    g.u0 = key; g.n = 1; g.detect = true; g.tma = ctx->lk_use_tma; g.s = st; g.max_pts = 0;
     g.launches = ctx->launches - before;
     VO_CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
