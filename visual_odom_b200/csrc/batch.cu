@@ -186,32 +186,40 @@ static int run_range_launch(vo_ctx* ctx, const View& v)
     ctx->imgs_per_unit = 4;
     int rc;
     int c = -1;
-    if (ctx->use_priorities)
-        for (int k = 0; k < 2; k++) if (ctx->side_stream[k] && v.s == ctx->side_stream[k]) c = k;
-    View h = v;                                  // the view the helper kernels run on
-    if (c >= 0) {
+    for (int k = 0; k < 2; k++) if (ctx->side_stream[k] && v.s == ctx->side_stream[k]) c = k;
+    // With the SM partition on, a side-stream range runs its LK ring on the LK partition's stream and everything else on the
+    // helper partition's stream; otherwise (priorities) everything but the LK ring goes to the side stream's high-priority helper.
+    const bool part = ctx->part_on && c >= 0;
+    const bool prio = !part && ctx->use_priorities && c >= 0;
+    View h = v, lk = v;                          // the views the helper kernels / the LK ring run on
+    cudaEvent_t* ev = nullptr;
+    if (part) {
+        h.s = ctx->part_hp_stream[c]; lk.s = ctx->part_lk_stream[c]; ev = ctx->part_ev[c];
+    } else if (prio) {
         if ((rc = ensure_hi_streams(ctx))) return rc;
-        h.s = ctx->hi_stream[c];
-        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][0], v.s));
-        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ctx->hi_ev[c][0], 0));
+        h.s = ctx->hi_stream[c]; ev = ctx->hi_ev[c];
+    }
+    if (ev) {
+        VO_CUDA_CHECK(cudaEventRecord(ev[0], v.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ev[0], 0));
     }
     if (ctx->batch_detect) {
         if ((rc = vo_run_fast(ctx, h, 0, false))) return rc;
         if ((rc = vo_run_select(ctx, h))) return rc;
     }
     if ((rc = vo_run_pyramid(ctx, v.u0 * ctx->imgs_per_unit, v.n * ctx->imgs_per_unit, h.s))) return rc;
-    if (c >= 0) {
-        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][1], h.s));
-        VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ctx->hi_ev[c][1], 0));
+    if (ev) {
+        VO_CUDA_CHECK(cudaEventRecord(ev[1], h.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(lk.s, ev[1], 0));
     }
     const int ip[4] = {0, 1, 3, 2}, in[4] = {1, 3, 2, 0};      // ring L0->R0->R1->L1->L0 (planes L0,R0,L1,R1)
     ctx->lk_per_unit = ctx->batch_max_pts;                      // no unit of the resident batch has more live features
-    rc = vo_run_lk_ring(ctx, v, 4, ip, in, false);
+    rc = vo_run_lk_ring(ctx, lk, 4, ip, in, false);
     ctx->lk_per_unit = 0;
     if (rc) return rc;
-    if (c >= 0) {
-        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][2], v.s));
-        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ctx->hi_ev[c][2], 0));
+    if (ev) {
+        VO_CUDA_CHECK(cudaEventRecord(ev[2], lk.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(h.s, ev[2], 0));
     }
     if ((rc = vo_run_filter(ctx, h, false))) return rc;
     const size_t cs = (size_t)ctx->units * ctx->cap;
@@ -222,9 +230,9 @@ static int run_range_launch(vo_ctx* ctx, const View& v)
                                                   ctx->d_n5 + v.u0, v.n, ctx->batch_detect ? 1 : 0);
     ctx->launches += 1;
     VO_CUDA_CHECK(cudaGetLastError());
-    if (c >= 0) {                                // join: later work on v.s (result copy, the next submission) sees everything
-        VO_CUDA_CHECK(cudaEventRecord(ctx->hi_ev[c][3], h.s));
-        VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ctx->hi_ev[c][3], 0));
+    if (ev) {                                    // join: later work on v.s (result copy, the next submission) sees everything
+        VO_CUDA_CHECK(cudaEventRecord(ev[3], h.s));
+        VO_CUDA_CHECK(cudaStreamWaitEvent(v.s, ev[3], 0));
     }
     return VO_OK;
 }
@@ -239,7 +247,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     // on a side stream with priorities enabled are launched plainly unless "batch_graphs" forces graphs.
     bool on_side = false;
     for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
-    if (!ctx->use_graphs || (ctx->use_priorities && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
+    if (!ctx->use_graphs || ((ctx->use_priorities || ctx->part_on) && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
         if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma && g.s == v.s && g.max_pts == ctx->batch_max_pts) {
             VO_CUDA_CHECK(cudaGraphLaunch(g.exec, v.s));

@@ -81,6 +81,7 @@ extern "C" void vo_destroy(vo_ctx* ctx)
     vo_drain_pending(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     vo_dist_shutdown(ctx);
+    vo_partition_destroy(ctx);
     vo_free_state(ctx);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto& p : ctx->pending) if (p.done) cudaEventDestroy(p.done);
@@ -128,6 +129,7 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
     if (strcmp(key, "lk_ctas_per_sm") == 0) { ctx->lk_ctas_per_sm = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "batch_outputs") == 0) { ctx->batch_outputs = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
+    if (strcmp(key, "sm_partition") == 0) return vo_partition_enable(ctx, (int)value);
     if (strcmp(key, "lk_quota") == 0) { ctx->lk_quota = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_span") == 0) { ctx->lk_span = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_kernel") == 0) { ctx->lk_kernel = value == 3 ? 3 : 4; vo_drop_graphs(ctx); return VO_OK; }
@@ -179,6 +181,93 @@ int vo_claim_buffers(vo_ctx* ctx, const char* who, bool allow_pending_batches)
                 return VO_E_INVALID;
             }
     ctx->seq_active = false;        // the sequence's image planes and per-frame buffers are reused from here on: vo_seq_begin again
+    return VO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SM partition: two green contexts (CUDA driver API, resolved through the runtime so that the library does not link libcuda)
+typedef CUresult (*PFN_cuDeviceGet)(CUdevice*, int);
+typedef CUresult (*PFN_cuDeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType);
+typedef CUresult (*PFN_cuDevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+typedef CUresult (*PFN_cuDevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+typedef CUresult (*PFN_cuGreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*PFN_cuGreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int);
+typedef CUresult (*PFN_cuGreenCtxDestroy)(CUgreenCtx);
+
+template <typename F>
+static bool drv(const char* name, F* fn)
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return false;
+    *fn = (F)p;
+    return true;
+}
+
+void vo_partition_destroy(vo_ctx* ctx)
+{
+    for (int c = 0; c < 2; c++) {
+        if (ctx->part_lk_stream[c]) cudaStreamDestroy(ctx->part_lk_stream[c]);
+        if (ctx->part_hp_stream[c]) cudaStreamDestroy(ctx->part_hp_stream[c]);
+        ctx->part_lk_stream[c] = ctx->part_hp_stream[c] = nullptr;
+        for (int k = 0; k < 4; k++) if (ctx->part_ev[c][k]) { cudaEventDestroy(ctx->part_ev[c][k]); ctx->part_ev[c][k] = nullptr; }
+    }
+    PFN_cuGreenCtxDestroy destroy = nullptr;
+    if (drv("cuGreenCtxDestroy", &destroy))
+        for (int k = 0; k < 2; k++) if (ctx->part_gctx[k]) destroy((CUgreenCtx)ctx->part_gctx[k]);
+    ctx->part_gctx[0] = ctx->part_gctx[1] = nullptr;
+    ctx->part_on = false; ctx->part_helper_sms = ctx->part_lk_sms = 0;
+}
+
+int vo_partition_enable(vo_ctx* ctx, int helper_sms)
+{
+    VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    int rc = vo_drain_pending(ctx);
+    if (rc) return rc;
+    VO_CUDA_CHECK(cudaDeviceSynchronize());
+    vo_drop_graphs(ctx);
+    vo_partition_destroy(ctx);
+    if (helper_sms <= 0) return VO_OK;
+    PFN_cuDeviceGet dget; PFN_cuDeviceGetDevResource getres; PFN_cuDevSmResourceSplitByCount split;
+    PFN_cuDevResourceGenerateDesc gendesc; PFN_cuGreenCtxCreate create; PFN_cuGreenCtxStreamCreate screate;
+    if (!drv("cuDeviceGet", &dget) || !drv("cuDeviceGetDevResource", &getres) || !drv("cuDevSmResourceSplitByCount", &split) ||
+        !drv("cuDevResourceGenerateDesc", &gendesc) || !drv("cuGreenCtxCreate", &create) || !drv("cuGreenCtxStreamCreate", &screate)) {
+        vo_set_error(ctx, "sm_partition: this driver has no green-context API");
+        return VO_E_UNSUPPORTED;
+    }
+    CUdevice dev;
+    CUdevResource all, part[1], rest;
+    unsigned int nb = 1;
+    CUresult r;
+    if ((r = dget(&dev, ctx->device)) != CUDA_SUCCESS || (r = getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS ||
+        (r = split(part, &nb, &all, &rest, 0, (unsigned)helper_sms)) != CUDA_SUCCESS || nb != 1) {
+        vo_set_error(ctx, "sm_partition: splitting off %d SMs failed (driver error %d)", helper_sms, (int)r);
+        return VO_E_UNSUPPORTED;
+    }
+    CUdevResource* rs[2] = {&part[0], &rest};
+    for (int k = 0; k < 2; k++) {
+        CUdevResourceDesc desc;
+        CUgreenCtx g;
+        if ((r = gendesc(&desc, rs[k], 1)) != CUDA_SUCCESS || (r = create(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) {
+            vo_set_error(ctx, "sm_partition: cuGreenCtxCreate failed (driver error %d)", (int)r);
+            vo_partition_destroy(ctx);
+            return VO_E_UNSUPPORTED;
+        }
+        ctx->part_gctx[k] = g;
+    }
+    ctx->part_helper_sms = (int)part[0].sm.smCount; ctx->part_lk_sms = (int)rest.sm.smCount;
+    for (int c = 0; c < 2; c++) {
+        CUstream a, b;
+        if ((r = screate(&a, (CUgreenCtx)ctx->part_gctx[0], CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS ||
+            (r = screate(&b, (CUgreenCtx)ctx->part_gctx[1], CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
+            vo_set_error(ctx, "sm_partition: cuGreenCtxStreamCreate failed (driver error %d)", (int)r);
+            vo_partition_destroy(ctx);
+            return VO_E_UNSUPPORTED;
+        }
+        ctx->part_hp_stream[c] = (cudaStream_t)a; ctx->part_lk_stream[c] = (cudaStream_t)b;
+        for (int k = 0; k < 4; k++) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->part_ev[c][k], cudaEventDisableTiming));
+    }
+    ctx->part_on = true;
     return VO_OK;
 }
 
@@ -452,12 +541,16 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         a.per_unit = ctx->lk_per_unit > 0 && ctx->lk_per_unit < ctx->cap ? ctx->lk_per_unit : ctx->cap;
         a.progress = ctx->d_lk_progress + uo;
         {   // a launch with fewer features than resident warps gains nothing from splitting its rings
-            const long resident_warps = (long)ctx->sm_count * vo_lk_ctas_per_sm(ctx->lk_ctas_per_sm) * LK_WARPS_PER_CTA;
+            int lk_sms = ctx->sm_count;
+            for (int c = 0; c < 2; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
+            const long resident_warps = (long)lk_sms * vo_lk_ctas_per_sm(ctx->lk_ctas_per_sm) * LK_WARPS_PER_CTA;
             const bool big = (long)a.n_units * a.per_unit > resident_warps;
             a.span = ctx->lk_span > 0 ? ctx->lk_span : (big ? 2 : 0);
             a.quota = big ? ctx->lk_quota : 0;
         }
-        VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, ctx->sm_count, ctx->lk_ctas_per_sm, v.s));
+        int lk_sms = ctx->sm_count;
+        for (int c = 0; c < 2; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
+        VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, lk_sms, ctx->lk_ctas_per_sm, v.s));
     }
     ctx->launches += 1;
     if (e1) VO_CUDA_CHECK(cudaEventRecord(e1, v.s));

@@ -82,6 +82,15 @@ struct vo_ctx {
     double seq_pose[16] = {1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1};   // frame_pose of main.cpp:90, integrated per push
     uint8_t* d_bgr = nullptr;           // staging of colour (BGR) inputs, converted by k_bgr_to_gray (ingest.cu)
     size_t bgr_bytes = 0;
+    // SM partition (green contexts, ctx.cu vo_partition_enable): the LK ring kernel -- persistent, 100 % of the registers of
+    // every SM it runs on -- gets its own SMs, every other kernel of the batched path (FAST, pyramids, filters, triangulation,
+    // PnP) runs on the rest, so the helper kernels of one unit range execute WHILE the other range's LK ring does
+    bool part_on = false;
+    int part_helper_sms = 0, part_lk_sms = 0;
+    void* part_gctx[2] = {nullptr, nullptr};            // CUgreenCtx: [0] helpers, [1] LK
+    cudaStream_t part_lk_stream[2] = {nullptr, nullptr};     // per side stream
+    cudaStream_t part_hp_stream[2] = {nullptr, nullptr};
+    cudaEvent_t part_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     // multi-GPU record gather over NCCL (dist.cu); NCCL is dlopen'ed at vo_dist_init
     void* dist_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
@@ -158,6 +167,8 @@ void vo_set_calibration(vo_ctx* ctx, const float P_l[12], const float P_r[12]);
 int vo_drain_pending(vo_ctx* ctx);
 // Entry points that overwrite the shared image planes / unit-0 buffers call this first: refused (VO_E_INVALID) while
 // sequence frames or batch submissions are in flight; an idle sequence is ended (its planes are about to be reused).
+int vo_partition_enable(vo_ctx* ctx, int helper_sms);       // 0 = off
+void vo_partition_destroy(vo_ctx* ctx);
 int vo_dist_order_after_gathers(vo_ctx* ctx, cudaStream_t st);
 void vo_dist_shutdown(vo_ctx* ctx);
 int vo_claim_buffers(vo_ctx* ctx, const char* who, bool allow_pending_batches = false);

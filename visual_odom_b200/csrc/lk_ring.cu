@@ -50,6 +50,8 @@
 
 namespace {
 
+template <bool B> struct BoolC { static constexpr bool value = B; };
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -428,6 +430,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                 // ---- Newton iterations ------------------------------------------------------------
                 float pdx = 0.f, pdy = 0.f;
                 bool tile_valid = j_ok0;
+                bool force_replay = false;          // set by the first faithful replay of this level-solve
                 for (int j = 0; j < args.max_iters; j++) {
                     inx = __float2int_rd(npx); iny = __float2int_rd(npy);
                     if (inx < -VO_WIN || inx >= lw || iny < -VO_WIN || iny >= lh) {
@@ -458,7 +461,13 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     int sxs = 0, sys = 0, sxt = 0, syt = 0;         // signed sums: strip (my SIMD chain) / tail
                     unsigned axs = 0, ays = 0, axt = 0, ayt = 0;    // sums of |addend|
                     int dpk[8];                       // int16 residuals, two per register (same element order as the I patch)
-                    {
+                    // The residual pass.  WITH_SUMS: also the products with the gradients, their exact integer sums and the
+                    // sums of |addend| that decide whether the integer sums ARE the float32 chain sums.  Once an iteration of
+                    // a level needed the faithful replay the following ones nearly always do (oracle: 94 %), and the replay
+                    // recomputes the products from the residuals anyway -- so after a replay the rest of the level runs the
+                    // light pass and goes straight to the replay (always valid, only slower than the exact path).
+                    auto residual_pass = [&](auto with_sums) {
+                        constexpr bool WITH_SUMS = decltype(with_sums)::value;
                         if (!IN_REGS) {
                             const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
                             Ipk[0] = (int)i03.x; Ipk[1] = (int)i03.y; Ipk[2] = (int)i03.z; Ipk[3] = (int)i03.w;
@@ -478,11 +487,13 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                                 const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
                                 const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
                                 if (e & 1) dpk[e >> 1] |= diff << 16; else dpk[e >> 1] = diff & 0xffff;
-                                const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
-                                const int vy = diff * (dxy[e] >> 16);
-                                // |v| + acc in one VABSDIFF (|v| <= 2^28, 15 of them per lane: no overflow)
-                                if (part) { sxt += vx; syt += vy; axt = __sad(vx, 0, axt); ayt = __sad(vy, 0, ayt); }
-                                else { sxs += vx; sys += vy; axs = __sad(vx, 0, axs); ays = __sad(vy, 0, ays); }
+                                if (WITH_SUMS) {
+                                    const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
+                                    const int vy = diff * (dxy[e] >> 16);
+                                    // |v| + acc in one VABSDIFF (|v| <= 2^28, 15 of them per lane: no overflow)
+                                    if (part) { sxt += vx; syt += vy; axt = __sad(vx, 0, axt); ayt = __sad(vy, 0, ayt); }
+                                    else { sxs += vx; sys += vy; axs = __sad(vx, 0, axs); ays = __sad(vy, 0, ays); }
+                                }
                                 ptop = pbot;
                             }
                         }
@@ -490,18 +501,22 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                             dpk_s[lane] = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
                             dpk_s[32 + lane] = make_uint4(dpk[4], dpk[5], dpk[6], dpk[7]);
                         }
+                    };
+                    bool exact = false;
+                    if (force_replay) {
+                        residual_pass(BoolC<false>{});
+                    } else {
+                        residual_pass(BoolC<true>{});
+                        // per-chain totals (exact integers) and per-chain sums of |addend| (REDUX over the chain's lanes)
+                        const unsigned cax = chain_sum_u(axs), cay = chain_sum_u(ays);
+                        const unsigned tax = __reduce_add_sync(FULL, axt), tay = __reduce_add_sync(FULL, ayt);
+                        // |pair sum| <= |v0| + |v1|, so the bound is conservative for the SIMD chains
+                        exact = __all_sync(FULL, cax <= (1u << 24) && cay <= (1u << 24) && tax <= (1u << 24) && tay <= (1u << 24));
                     }
-                    // per-chain totals (exact integers) and per-chain sums of |addend| (REDUX over the chain's lanes)
-                    const unsigned cax = chain_sum_u(axs), cay = chain_sum_u(ays);
-                    const unsigned tax = __reduce_add_sync(FULL, axt), tay = __reduce_add_sync(FULL, ayt);
-                    // |pair sum| <= |v0| + |v1|, so the bound is conservative for the SIMD chains
-                    const bool exact = __all_sync(FULL, cax <= (1u << 24) && cay <= (1u << 24) && tax <= (1u << 24) && tay <= (1u << 24));
                     float ib1, ib2;
                     if (exact) {
                         // every partial sum of every chain is an exactly representable integer.
                         // chain c's total sits in lanes 2c (x) / 2c+1 (y): even lanes carry b1, odd lanes b2
-                        const int cs = (int)chain_sum_u((unsigned)(half ? sys : sxs) + 0u * 0);     // placeholder, see below
-                        (void)cs;
                         const float fx = (float)(int)chain_sum_u((unsigned)sxs), fy = (float)(int)chain_sum_u((unsigned)sys);
                         const float tx = (float)__reduce_add_sync(FULL, sxt), ty = (float)__reduce_add_sync(FULL, syt);
                         const float v = half ? fy : fx;
@@ -537,6 +552,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         }
                         __syncwarp();
                         float acc = 0.f;
+                        force_replay = true;
                         if (lane < 10) acc = run_chain<42>(run_slot, rc == 4);
                         const float tot = combine_chains(acc);
                         ib1 = __shfl_sync(FULL, tot, 0); ib2 = __shfl_sync(FULL, tot, 5);
