@@ -129,7 +129,11 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     if (strcmp(key, "lk_staging") == 0) { ctx->lk_use_tma = !(value >= 1); return VO_OK; }
     if (strcmp(key, "lk_ctas_per_sm") == 0) { ctx->lk_ctas_per_sm = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "batch_outputs") == 0) { ctx->batch_outputs = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
-    if (strcmp(key, "sm_partition") == 0) return vo_partition_enable(ctx, (int)value);
+    if (strcmp(key, "sm_partition") == 0) {          // k > 0: every helper kernel on k SMs; k < 0: only the kernels after the ring on |k| SMs
+        ctx->part_pre_with_lk = value < 0;
+        ctx->part_auto = false;
+        return vo_partition_enable(ctx, value < 0 ? (int)-value : (int)value);
+    }
     if (strcmp(key, "lk_quota") == 0) { ctx->lk_quota = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_span") == 0) { ctx->lk_span = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_kernel") == 0) { ctx->lk_kernel = value == 3 ? 3 : 4; vo_drop_graphs(ctx); return VO_OK; }

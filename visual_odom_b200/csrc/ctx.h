@@ -86,6 +86,9 @@ struct vo_ctx {
     // every SM it runs on -- gets its own SMs, every other kernel of the batched path (FAST, pyramids, filters, triangulation,
     // PnP) runs on the rest, so the helper kernels of one unit range execute WHILE the other range's LK ring does
     bool part_on = false;
+    bool part_auto = true;              // the first vo_batch_submit turns the partition on (8 SMs for the kernels after the ring)
+    bool part_pre_with_lk = false;      // FAST / pyramids (throughput kernels) stay on the LK partition, only the latency-bound
+                                        // kernels after the ring (filters, triangulation, PnP) go to the small one
     int part_helper_sms = 0, part_lk_sms = 0;
     void* part_gctx[2] = {nullptr, nullptr};            // CUgreenCtx: [0] helpers, [1] LK
     cudaStream_t part_lk_stream[2] = {nullptr, nullptr};     // per side stream
