@@ -726,7 +726,7 @@ def main():
                 ctx = Context(local_rank, max_features=8192, max_units=2 * B)
                 ctx.set_stream(stream.cuda_stream)
 
-                def run_point(us_pinned, feats, b, w, h, Pm, steps=5):
+                def run_point(us_pinned, feats, b, w, h, Pm, steps=10):
                     q = Point(ctx, torch, stream, flush, us_pinned[:b], feats, b, w, h, Pm["P_l"], Pm["P_r"], barrier, 1)
                     r_ms, r_res, _l = q.measure_resident(steps, 3, 3)
                     lk_a, _lm, t_s, nf = q.measure_lk_alone(steps, 3)

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
-for v in 4 4:8; do
-  tag=$(echo $v | tr ':' '_')
-  LK_KERNELS=$v timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_lk_ring -s 3 -c 1 -f -o gpurun_out/lk_r2a_$tag python tools/lk_ab.py 4 2000 1 > gpurun_out/ncu_$tag.out 2>&1
-  tail -2 gpurun_out/ncu_$tag.out
-done
+nvidia-smi --query-gpu=index,name --format=csv
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_r2_n2.json 2> gpurun_out/bench_r2_n2.err
+echo rc=$?; tail -c 1500 gpurun_out/bench_r2_n2.err; head -c 600 gpurun_out/bench_r2_n2.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 20 --warmup 3 --cpu-seconds 3 > gpurun_out/bench_r2_ref_n2.json 2> gpurun_out/bench_r2_ref_n2.err
+echo rc=$?; head -c 300 gpurun_out/bench_r2_ref_n2.json

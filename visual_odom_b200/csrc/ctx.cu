@@ -70,6 +70,8 @@ extern "C" int vo_create(int device, const vo_params* params, vo_ctx** out)
         ctx->lk_use_tma = !(st && strcmp(st, "ldg") == 0);
         const char* sp = getenv("VO_LK_SPAN");      // force the LK work-item size (tests run the whole suite at 1)
         if (sp) ctx->lk_span = atoi(sp);
+        const char* pt = getenv("VO_SM_PARTITION");  // 0: never partition the SMs (profilers cannot attach to green-context launches)
+        if (pt && atoi(pt) == 0) ctx->part_auto = false;
     }
     return VO_OK;
 }
