@@ -645,7 +645,7 @@ def main():
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    for opt in ("graphs", "priorities", "batch_graphs", "lk_span", "lk_ctas_per_sm", "lk_kernel", "lk_quota", "sm_partition"):   # A/B switches, e.g. VO_OPT_LK_SPAN=16
+    for opt in ("graphs", "priorities", "batch_graphs", "lk_span", "lk_ctas_per_sm", "lk_quota", "sm_partition"):   # A/B switches, e.g. VO_OPT_LK_SPAN=16
         if os.environ.get("VO_OPT_" + opt.upper()) is not None:
             ctx.set_option(opt, float(os.environ["VO_OPT_" + opt.upper()]))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""A/B of the LK ring kernel versions on the bench workload (one GPU, single stream, plain launches):
-  python tools/lk_ab.py [units] [features] [steps]
-For each kernel (3 = round-1 one-CTA-per-feature kernel, 4 = persistent warps) prints the average CUDA-event
-time of the LK launch, and checks that both produce identical point lists / status (bit-exact).
+"""A/B of the LK ring kernel's instantiations / work-item sizes on the bench workload (one GPU, single stream, plain launches):
+  LK_KERNELS=4:8:2,4:12:2 python tools/lk_ab.py [units] [features] [steps]      (4:<CTAs per SM>:<phases per work item>)
+Prints the average CUDA-event time of the LK launch per configuration and checks that all of them produce identical
+point lists / inlier lists (bit-exact).
 """
 import json
 import os
@@ -16,7 +16,7 @@ from visual_odom_b200.capi import Context
 units = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 feats = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-kernels = os.environ.get("LK_KERNELS", "3,4:12:16,4:8:16,4:12:1,4:10:1,4:8:1,4:12:4,4:8:4").split(",")      # kernel[:ctas_per_sm[:span]]
+kernels = os.environ.get("LK_KERNELS", "4:8:2,4:8:16,4:8:1,4:8:4,4:10:2,4:12:2").split(",")      # 4:ctas_per_sm:span (span 16 = one item per feature-ring)
 us = [synth.stereo_unit(1241, 376, s) for s in range(units)]
 ctx = Context(0, max_features=max(2048, feats), max_units=units)
 ctx.set_option("graphs", 0)
@@ -27,7 +27,6 @@ ctx.batch_upload(arr, pitch)
 out = {}
 got = {}
 for k in kernels:
-    ctx.set_option("lk_kernel", int(k.split(":")[0]))
     kk = k.split(":")
     ctx.set_option("lk_ctas_per_sm", int(kk[1]) if len(kk) > 1 else 0)
     ctx.set_option("lk_span", int(kk[2]) if len(kk) > 2 else 0)

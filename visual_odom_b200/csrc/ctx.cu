@@ -138,7 +138,6 @@ extern "C" int vo_set_option(vo_ctx* ctx, const char* key, double value)
     }
     if (strcmp(key, "lk_quota") == 0) { ctx->lk_quota = (int)value; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "lk_span") == 0) { ctx->lk_span = (int)value; vo_drop_graphs(ctx); return VO_OK; }
-    if (strcmp(key, "lk_kernel") == 0) { ctx->lk_kernel = value == 3 ? 3 : 4; vo_drop_graphs(ctx); return VO_OK; }
     if (strcmp(key, "graphs") == 0) { ctx->use_graphs = value >= 1; return VO_OK; }
     if (strcmp(key, "batch_graphs") == 0) { ctx->batch_graphs = value >= 1; return VO_OK; }
     if (strcmp(key, "priorities") == 0) { ctx->use_priorities = value >= 1; vo_drop_graphs(ctx); return VO_OK; }
@@ -533,9 +532,7 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         ctx->ev_used += 2;
         VO_CUDA_CHECK(cudaEventRecord(e0, v.s));
     }
-    if (ctx->lk_kernel == 3) {
-        VO_CUDA_CHECK(vo_launch_lk_ring_v3(ctx->maps, a, v.s));
-    } else {
+    {
         // the queue pair of the launching stream
         size_t qi = 0;
         while (qi < ctx->lk_queue_streams.size() && ctx->lk_queue_streams[qi] != v.s) qi++;

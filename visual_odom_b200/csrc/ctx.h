@@ -127,7 +127,6 @@ struct vo_ctx {
     int lk_span = 0;                    // phases per LK work item: 0 = automatic (one level-solve per item when a launch has
                                         // more features than resident warps, else one item per feature-ring)
     int* d_lk_progress = nullptr;       // [units][cap] hand-over counters of the LK work items (zero between launches)
-    int lk_kernel = 4;                  // 3 = the round-1 kernel (A/B measurement only)
     int lk_per_unit = 0;                // upper bound of live features per unit known to the host (0 = cap)
     // work queues of the persistent LK warps: one (next, dry) pair per stream that launches the kernel,
     // so launches of different streams never share a pair; a pair resets itself at the end of a launch

@@ -37,25 +37,12 @@ __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* const* __rest
         const int v = p[0];
         int d[16];
         unsigned hi = 0, lo = 0;
-        // quick reject on the four compass pixels: an arc of 9 contiguous ring pixels holds at least two of them
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) {
+        for (int k = 0; k < 16; k++) {
             const int r = p[c_ring_dy[k] * pitch + c_ring_dx[k]];
             d[k] = v - r;
             hi |= (unsigned)(r > v + threshold) << k;
             lo |= (unsigned)(r < v - threshold) << k;
-        }
-        if (__popc(hi) >= 2 || __popc(lo) >= 2) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                if ((k & 3) == 0) continue;
-                const int r = p[c_ring_dy[k] * pitch + c_ring_dx[k]];
-                d[k] = v - r;
-                hi |= (unsigned)(r > v + threshold) << k;
-                lo |= (unsigned)(r < v - threshold) << k;
-            }
-        } else {
-            hi = lo = 0;
         }
         // >= 9 contiguous set bits on the 16-cycle
         unsigned mh = hi | (hi << 16), ml = lo | (lo << 16);
@@ -84,6 +71,7 @@ __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* const* __rest
 }
 
 #define NMS_T 256
+#define NMS_NC 8                 // chunks of NMS_T pixels handled per pass: one pass covers rows up to 2048 pixels
 __global__ void __launch_bounds__(NMS_T) k_fast_nms_row(const uint8_t* __restrict__ score, size_t score_plane, int w, int h,
                                                         int nonmax, uint16_t* __restrict__ rowbuf, int rowcap,
                                                         int* __restrict__ rowcount)
@@ -91,19 +79,19 @@ __global__ void __launch_bounds__(NMS_T) k_fast_nms_row(const uint8_t* __restric
     const int y = blockIdx.x, unit = blockIdx.y;
     const uint8_t* __restrict__ sc = score + (size_t)unit * score_plane;
     uint16_t* __restrict__ out = rowbuf + ((size_t)unit * h + y) * rowcap;
-    __shared__ uint8_t rows[3][NMS_T + 2];
-    __shared__ int wcnt[NMS_T / 32];
+    __shared__ uint8_t rows[3][NMS_T * NMS_NC + 2];
+    __shared__ int wcnt[NMS_NC * (NMS_T / 32)];         // survivors per (chunk, warp), then their exclusive prefix
     __shared__ int base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
     if (y < 3 || y >= h - 3) {                     // border rows hold no corners
         if (threadIdx.x == 0) rowcount[unit * h + y] = 0;
         return;
     }
+    if (threadIdx.x == 0) base = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int x0 = 0; x0 < w; x0 += NMS_T) {
-        // stage the three score rows (with a 1-pixel halo) in shared memory
-        for (int i = threadIdx.x; i < NMS_T + 2; i += NMS_T) {
+    constexpr int NW = NMS_T / 32, SPAN = NMS_T * NMS_NC;
+    for (int x0 = 0; x0 < w; x0 += SPAN) {
+        // stage the three score rows (with a 1-pixel halo) in shared memory: the whole pass at once
+        for (int i = threadIdx.x; i < SPAN + 2; i += NMS_T) {
             const int x = x0 - 1 + i;
             const bool in = (x >= 0 && x < w);
             rows[0][i] = in ? sc[(size_t)(y - 1) * w + x] : 0;
@@ -111,31 +99,52 @@ __global__ void __launch_bounds__(NMS_T) k_fast_nms_row(const uint8_t* __restric
             rows[2][i] = in ? sc[(size_t)(y + 1) * w + x] : 0;
         }
         __syncthreads();
-        const int x = x0 + threadIdx.x, i = threadIdx.x + 1;
-        bool keep = false;
-        if (x < w) {
-            const int s = rows[1][i];
-            if (s > 0) {
-                keep = !nonmax ||
-                       (s > rows[1][i - 1] && s > rows[1][i + 1] && s > rows[0][i - 1] && s > rows[0][i] &&
-                        s > rows[0][i + 1] && s > rows[2][i - 1] && s > rows[2][i] && s > rows[2][i + 1]);
+        unsigned bal[NMS_NC];
+#pragma unroll
+        for (int c = 0; c < NMS_NC; c++) {
+            const int x = x0 + c * NMS_T + threadIdx.x, i = c * NMS_T + threadIdx.x + 1;
+            bool keep = false;
+            if (x < w) {
+                const int s = rows[1][i];
+                if (s > 0) {
+                    keep = !nonmax ||
+                           (s > rows[1][i - 1] && s > rows[1][i + 1] && s > rows[0][i - 1] && s > rows[0][i] &&
+                            s > rows[0][i + 1] && s > rows[2][i - 1] && s > rows[2][i] && s > rows[2][i + 1]);
+                }
+            }
+            bal[c] = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) wcnt[c * NW + warp] = __popc(bal[c]);
+        }
+        __syncthreads();
+        // exclusive prefix over the (chunk, warp) counts in x order: 64 entries, two warps
+        int carry_total = 0;
+        if (threadIdx.x < NMS_NC * NW) {
+            const int v = wcnt[threadIdx.x];
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            carry_total = incl;                     // lane 31 of each of the two warps holds its warp's total
+            wcnt[threadIdx.x] = incl - v;
+        }
+        __shared__ int w0_total, pass_total;
+        if (threadIdx.x == 31) w0_total = carry_total;
+        __syncthreads();
+        if (threadIdx.x >= 32 && threadIdx.x < NMS_NC * NW) wcnt[threadIdx.x] += w0_total;
+        if (threadIdx.x == NMS_NC * NW - 1) pass_total = carry_total + w0_total;
+        __syncthreads();
+        const int b0 = base;
+#pragma unroll
+        for (int c = 0; c < NMS_NC; c++) {
+            if ((bal[c] >> lane) & 1u) {
+                const int o = b0 + wcnt[c * NW + warp] + __popc(bal[c] & ((1u << lane) - 1u));
+                if (o < rowcap) out[o] = (uint16_t)(x0 + c * NMS_T + threadIdx.x);
             }
         }
-        const unsigned b = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) wcnt[warp] = __popc(b);
         __syncthreads();
-        int off = base;
-        for (int k = 0; k < warp; k++) off += wcnt[k];
-        if (keep) {
-            const int o = off + __popc(b & ((1u << lane) - 1u));
-            if (o < rowcap) out[o] = (uint16_t)x;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int k = 0; k < NMS_T / 32; k++) t += wcnt[k];
-            base += t;
-        }
+        if (threadIdx.x == 0) base = b0 + pass_total;
         __syncthreads();
     }
     if (threadIdx.x == 0) rowcount[unit * h + y] = base < rowcap ? base : rowcap;

@@ -468,7 +468,6 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                     // light pass and goes straight to the replay (always valid, only slower than the exact path).
                     auto residual_pass = [&](auto with_sums) {
                         constexpr bool WITH_SUMS = decltype(with_sums)::value;
-                        constexpr bool DIRECT = !WITH_SUMS;        // forced replay: the float addends go straight to the chain slots
                         if (!IN_REGS) {
                             const uint4 i03 = ipk_s[lane], i47 = ipk_s[32 + lane];
                             Ipk[0] = (int)i03.x; Ipk[1] = (int)i03.y; Ipk[2] = (int)i03.z; Ipk[3] = (int)i03.w;
@@ -487,22 +486,10 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                                 const int e = part ? 11 + k : k;
                                 const int Iv = (e & 1) ? (Ipk[e >> 1] >> 16) : (int)(short)(Ipk[e >> 1] & 0xffff);
                                 const int diff = (dp2a_taps(wb, pbot, dp2a_taps(wt, ptop, 1 << (W_BITS - 6))) >> (W_BITS - 5)) - Iv;
-                                if (!DIRECT) { if (e & 1) dpk[e >> 1] |= diff << 16; else dpk[e >> 1] = diff & 0xffff; }
-                                const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
-                                const int vy = diff * (dxy[e] >> 16);
-                                if (DIRECT) {
-                                    if (!part) {
-                                        const int px2 = vx + __shfl_down_sync(FULL, vx, 8), py2 = vy + __shfl_down_sync(FULL, vy, 8);   // + column x+4
-                                        if (!(cpos & 1) && (k < 10 || half)) {
-                                            sm.chain[b_pos + k * 2] = (float)px2;
-                                            sm.chain[QSTRIDE + b_pos + k * 2] = (float)py2;
-                                        }
-                                    } else if (k < tn) {
-                                        sm.chain[t_pos + k * 5] = (float)vx;
-                                        sm.chain[QSTRIDE + t_pos + k * 5] = (float)vy;
-                                    }
-                                }
+                                if (e & 1) dpk[e >> 1] |= diff << 16; else dpk[e >> 1] = diff & 0xffff;
                                 if (WITH_SUMS) {
+                                    const int vx = diff * (int)(short)(dxy[e] & 0xffff);      // gradients are 0 for dummy elements
+                                    const int vy = diff * (dxy[e] >> 16);
                                     // |v| + acc in one VABSDIFF (|v| <= 2^28, 15 of them per lane: no overflow)
                                     if (part) { sxt += vx; syt += vy; axt = __sad(vx, 0, axt); ayt = __sad(vy, 0, ayt); }
                                     else { sxs += vx; sys += vy; axs = __sad(vx, 0, axs); ays = __sad(vy, 0, ays); }
@@ -510,7 +497,7 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                                 ptop = pbot;
                             }
                         }
-                        if (!IN_REGS && !DIRECT) {
+                        if (!IN_REGS) {
                             dpk_s[lane] = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
                             dpk_s[32 + lane] = make_uint4(dpk[4], dpk[5], dpk[6], dpk[7]);
                         }
@@ -539,8 +526,6 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                         ib1 = __shfl_sync(FULL, tot, 0); ib2 = __shfl_sync(FULL, tot, 1);
                     } else {
                         // faithful replay: float addends in chain order, runner lanes add them
-                        // (a forced-replay pass has already written them)
-                        if (!force_replay) {
                         if (!IN_REGS) {
                             const uint4 d03 = dpk_s[lane], d47 = dpk_s[32 + lane];
                             dpk[0] = (int)d03.x; dpk[1] = (int)d03.y; dpk[2] = (int)d03.z; dpk[3] = (int)d03.w;
@@ -564,7 +549,6 @@ k_lk_ring(const __grid_constant__ LkMaps maps, const LkArgs args)
                                 sm.chain[t_pos + k * 5] = (float)(d * (int)(short)(dxy[e] & 0xffff));
                                 sm.chain[QSTRIDE + t_pos + k * 5] = (float)(d * (dxy[e] >> 16));
                             }
-                        }
                         }
                         __syncwarp();
                         float acc = 0.f;
@@ -696,17 +680,13 @@ cudaError_t vo_lk_prepare()
     if ((e = prep<false, LK_CTAS_PER_SM>()) != cudaSuccess) return e;
     if ((e = prep<true, 12>()) != cudaSuccess) return e;
     if ((e = prep<true, 10>()) != cudaSuccess) return e;
-    if ((e = prep<true, 9>()) != cudaSuccess) return e;
     if ((e = prep<true, 8>()) != cudaSuccess) return e;
-    if ((e = prep<true, 7>()) != cudaSuccess) return e;
-    if ((e = prep<true, 6>()) != cudaSuccess) return e;
-    if ((e = prep<true, 5>()) != cudaSuccess) return e;
-    return vo_lk_prepare_v3();
+    return cudaSuccess;
 }
 
 int vo_lk_ctas_per_sm(int requested)
 {
-    return (requested == 12 || requested == 10 || (requested >= 5 && requested <= 9)) ? requested : LK_CTAS_PER_SM;
+    return (requested == 12 || requested == 10 || requested == 8) ? requested : LK_CTAS_PER_SM;
 }
 
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream)
@@ -730,10 +710,6 @@ cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_cou
     if (!args.use_tma) k_lk_ring<false, LK_CTAS_PER_SM><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else if (cps == 12) k_lk_ring<true, 12><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else if (cps == 10) k_lk_ring<true, 10><<<(int)ctas, thr, sh, stream>>>(maps, args);
-    else if (cps == 9) k_lk_ring<true, 9><<<(int)ctas, thr, sh, stream>>>(maps, args);
-    else if (cps == 7) k_lk_ring<true, 7><<<(int)ctas, thr, sh, stream>>>(maps, args);
-    else if (cps == 6) k_lk_ring<true, 6><<<(int)ctas, thr, sh, stream>>>(maps, args);
-    else if (cps == 5) k_lk_ring<true, 5><<<(int)ctas, thr, sh, stream>>>(maps, args);
     else k_lk_ring<true, 8><<<(int)ctas, thr, sh, stream>>>(maps, args);
     return cudaGetLastError();
 }

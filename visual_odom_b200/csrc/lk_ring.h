@@ -2,8 +2,9 @@
 #pragma once
 #include "common.cuh"
 
-// Resident warps per SM the kernel is built for: 12 persistent CTAs of 2 warps (<= 80 registers per thread,
-// 8960 B of shared memory per warp: 12 x (2 x 8960 + 1024 reserved) = 227 328 B of the SM's 233 472 B).
+// The kernel is built for 8 persistent CTAs of 2 warps per SM (128 registers per thread: the whole register file) and, for
+// A/B measurement, for 10 and 12 (96 / 80 registers; 8960 B of shared memory per warp: 12 x (2 x 8960 + 1024 reserved) =
+// 227 328 B of the SM's 233 472 B).
 #define LK_WARPS_PER_CTA 2
 #define LK_CTAS_PER_SM 8
 
@@ -50,10 +51,7 @@ struct LkArgs {
 size_t vo_lk_smem_bytes();
 cudaError_t vo_lk_prepare();
 // sm_count sizes the persistent grid (CTAs = min(needed, sm_count * LK_CTAS_PER_SM))
-// ctas_per_sm: 0 = LK_CTAS_PER_SM; 10 / 8 select the instantiations built with more registers (A/B measurement)
+// ctas_per_sm: 0 = LK_CTAS_PER_SM; 10 / 12 select the instantiations built with fewer registers (A/B measurement)
 cudaError_t vo_launch_lk_ring(const LkMaps& maps, const LkArgs& args, int sm_count, int ctas_per_sm, cudaStream_t stream);
-// round-1 kernel (one single-warp CTA per feature), kept for A/B measurement only
 int vo_lk_ctas_per_sm(int requested);     // the instantiation a request maps to
-cudaError_t vo_lk_prepare_v3();
-cudaError_t vo_launch_lk_ring_v3(const LkMaps& maps, const LkArgs& args, cudaStream_t stream);
 int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int src_pitch, cudaStream_t stream);

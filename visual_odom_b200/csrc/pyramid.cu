@@ -19,6 +19,7 @@ static __device__ __forceinline__ uint32_t ldw(const uint8_t* p) { return __ldg(
 // ---------------------------------------------------------------------------------------------
 // raw (pitch = src_pitch) -> padded level 0.  grid.z = image index.
 // src images are addressed through a pointer table (one entry per image).
+#define PAD_ROWS 4
 __global__ void k_pad_level0(const uint8_t* const* __restrict__ src_tab, int src_pitch,
                              LevelGeom g)
 {
@@ -27,30 +28,43 @@ __global__ void k_pad_level0(const uint8_t* const* __restrict__ src_tab, int src
     uint8_t* __restrict__ dst = g.img + (size_t)img * g.plane;
     const int wq = g.pitch >> 2;                       // 4-pixel groups per padded row
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int Y = blockIdx.y;                          // padded row
     if (q >= wq) return;
-    const int sy = vo_reflect101(Y - VO_PAD, g.h);
-    const uint8_t* srow = src + (size_t)sy * src_pitch;
-    uint32_t out = 0;
+    int sx[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int X = 4 * q + i;
-        int sx = vo_reflect101(X - VO_PAD, g.w);
-        out |= (uint32_t)__ldg(srow + sx) << (8 * i);
+    for (int i = 0; i < 4; i++) sx[i] = vo_reflect101(4 * q + i - VO_PAD, g.w);
+    // PAD_ROWS padded rows per thread: fewer, longer-lived blocks and 4 x PAD_ROWS loads in flight
+    uint32_t out[PAD_ROWS];
+#pragma unroll
+    for (int r = 0; r < PAD_ROWS; r++) {
+        const int Y = blockIdx.y * PAD_ROWS + r;           // padded row
+        out[r] = 0;
+        if (Y < g.hp) {
+            const uint8_t* srow = src + (size_t)vo_reflect101(Y - VO_PAD, g.h) * src_pitch;
+#pragma unroll
+            for (int i = 0; i < 4; i++) out[r] |= (uint32_t)__ldg(srow + sx[i]) << (8 * i);
+        }
     }
-    *reinterpret_cast<uint32_t*>(dst + (size_t)Y * g.pitch + 4 * q) = out;
+#pragma unroll
+    for (int r = 0; r < PAD_ROWS; r++) {
+        const int Y = blockIdx.y * PAD_ROWS + r;
+        if (Y < g.hp) *reinterpret_cast<uint32_t*>(dst + (size_t)Y * g.pitch + 4 * q) = out[r];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // One launch per level l:  (a) Scharr derivative of level l (interior),
 //                          (b) if has_next: pyrDown level l -> padded level l+1.
 // grid.x covers max(work_a, work_b) in units of 4 horizontally adjacent output pixels.
+#define PYR_ROWS 1
 __global__ void k_pyr_level(LevelGeom s, LevelGeom d, int has_next)
 {
     const int img = blockIdx.z;
     const uint8_t* __restrict__ sp = s.img + (size_t)img * s.plane + (size_t)VO_PAD * s.pitch + VO_PAD; // pixel (0,0)
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = blockIdx.y;
+    // PYR_ROWS rows per thread (independent: the loads of all of them are in flight together, half as many blocks)
+#pragma unroll
+    for (int rr = 0; rr < PYR_ROWS; rr++) {
+    const int row = blockIdx.y * PYR_ROWS + rr;
 
     // (a) derivative of level s: rows [0,h), 4 pixels per thread.  The six bytes x0-1 .. x0+4 of a row come from three
     // aligned words (x0 and the row base are multiples of 4; the padding keeps x0-4 and x0+7 inside the plane).
@@ -138,6 +152,7 @@ __global__ void k_pyr_level(LevelGeom s, LevelGeom d, int has_next)
             *reinterpret_cast<uint32_t*>(dst + 4 * q) = out;
         }
     }
+    }   // rows of this thread
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -150,7 +165,7 @@ int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int 
     {
         const LevelGeom& g = pg.lv[0];
         dim3 block(128, 1, 1);
-        dim3 grid(((g.pitch >> 2) + block.x - 1) / block.x, g.hp, pg.n_img);
+        dim3 grid(((g.pitch >> 2) + block.x - 1) / block.x, (g.hp + PAD_ROWS - 1) / PAD_ROWS, pg.n_img);
         k_pad_level0<<<grid, block, 0, stream>>>(src_tab_dev, src_pitch, g);
         launches++;
     }
@@ -165,7 +180,7 @@ int vo_launch_pyramid(const PyrGeom& pg, const uint8_t* const* src_tab_dev, int 
             if (d.hp > rows) rows = d.hp;
         }
         dim3 block(128, 1, 1);
-        dim3 grid((qa + block.x - 1) / block.x, rows, pg.n_img);
+        dim3 grid((qa + block.x - 1) / block.x, (rows + PYR_ROWS - 1) / PYR_ROWS, pg.n_img);
         k_pyr_level<<<grid, block, 0, stream>>>(s, d, has_next);
         launches++;
     }
