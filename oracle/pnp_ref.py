@@ -707,17 +707,95 @@ def lm_refine(X, x, K, rvec0, tvec0, max_iter=20, eps=FLT_EPS):
     return param[:3].copy(), param[3:].copy()
 
 
+# ----------------------------------------------------------------------------- n == 4: the P3P case
+def p3p_solutions(X, y):
+    """All poses (R, t) with positive depths of three world points X (3 x 3) seen at normalised coordinates y (3 x 2).
+    Grunert's formulation (s2 = u s1, s3 = v s1, quartic in v built from polynomial products); the solution SET is what
+    cv::solveP3P returns (checked in tests/test_oracle_pnp.py), not its operation order."""
+    X = np.asarray(X, np.float64)
+    f = np.concatenate([np.asarray(y, np.float64), np.ones((3, 1))], 1)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    a2 = np.sum((X[1] - X[2]) ** 2); b2 = np.sum((X[0] - X[2]) ** 2); c2 = np.sum((X[0] - X[1]) ** 2)
+    if not b2 > 0:
+        return []
+    ca, cb, cg = f[1] @ f[2], f[0] @ f[2], f[0] @ f[1]
+    Kq = (a2 - c2) / b2
+    N = np.array([Kq + 1, -2 * Kq * cb, Kq - 1])          # ascending powers of v
+    D = np.array([2 * cg, -2 * ca])
+    Q = np.array([1, -2 * cb, 1])
+    pm = np.polynomial.polynomial.polymul
+    D2 = pm(D, D)
+    poly = np.zeros(5)
+    for term in (D2, pm(N, N), -2 * cg * pm(N, D), -(c2 / b2) * pm(Q, D2)):
+        poly[:len(term)] += term
+    if not np.all(np.isfinite(poly)):
+        return []
+
+    def frame(A):
+        e1 = A[1] - A[0]; e1 = e1 / np.linalg.norm(e1)
+        e3 = np.cross(e1, A[2] - A[0]); e3 = e3 / np.linalg.norm(e3)
+        return np.stack([e1, np.cross(e3, e1), e3], 1)
+
+    sols = []
+    for r in np.roots(np.trim_zeros(poly[::-1], "f")):
+        v = r.real
+        if abs(r.imag) > 1e-9 * max(1.0, abs(v)) or not v > 0:
+            continue
+        Dv = D[0] + D[1] * v
+        if abs(Dv) < 1e-12:
+            continue
+        u = (N[0] + N[1] * v + N[2] * v * v) / Dv
+        q = 1 + v * v - 2 * v * cb
+        if not (u > 0 and q > 0):
+            continue
+        s1 = np.sqrt(b2 / q)
+        P = f * np.array([s1, u * s1, v * s1])[:, None]
+        R = frame(P) @ frame(X).T
+        t = P[0] - R @ X[0]
+        if np.all(np.isfinite(R)) and np.all(np.isfinite(t)):
+            sols.append((R, t))
+    return sols
+
+
+def p3p_four_points(X, x, K):
+    """cv::solvePnPRansac with exactly four points (modules/calib3d solvepnp.cpp: model_points = 4, SOLVEPNP_P3P, a single
+    cv::solvePnP on all four, no RANSAC, no refinement): P3P on the first three points -- image points normalised as
+    cv::undistortPoints stores them (f32) -- and the fourth picks the solution by its squared pixel reprojection error.
+    Returns (rvec, tvec) or None.  Pinned against cv2 to 1e-5 (the f32 normalisation is what bounds it)."""
+    X = np.asarray(X, np.float32).reshape(4, 3).astype(np.float64)
+    x32 = np.asarray(x, np.float32).reshape(4, 2)
+    K64 = np.asarray(K, np.float64)
+    fx, fy, cx, cy = K64[0, 0], K64[1, 1], K64[0, 2], K64[1, 2]
+    yn = undistort_normalize_f32(x32, K64).astype(np.float64)
+    xp = x32.astype(np.float64)
+    best = None
+    for R, t in p3p_solutions(X[:3], yn[:3]):
+        Xc = R @ X[3] + t
+        e = (cx + fx * Xc[0] / Xc[2] - xp[3, 0]) ** 2 + (cy + fy * Xc[1] / Xc[2] - xp[3, 1]) ** 2
+        if np.isfinite(e) and (best is None or e < best[0]):
+            best = (e, R, t)
+    if best is None:
+        return None
+    return rodrigues_inv(best[1]), best[2]
+
+
 # ----------------------------------------------------------------------------- solvePnPRansac
 def solve_pnp_ransac(X, x, K, rvec0, tvec0, iterations=500, reproj=0.5, confidence=0.999, trace=None,
                      model_fn=None):
-    """cv::solvePnPRansac(..., useExtrinsicGuess=true, SOLVEPNP_ITERATIVE) for >= 5 points.
+    """cv::solvePnPRansac(..., useExtrinsicGuess=true, SOLVEPNP_ITERATIVE); n == 4 is the P3P case above.
     model_fn(Xs, xs, K) -> (rvec, tvec) defaults to the EPnP restatement."""
     X = np.asarray(X, np.float32).reshape(-1, 3)
     x = np.asarray(x, np.float32).reshape(-1, 2)
     K64 = np.asarray(K, np.float32).astype(np.float64)
     n = len(X)
     model_fn = model_fn or epnp
-    assert n >= 5, "this restatement covers the 5-point EPnP kernel path (n > 4)"
+    if n == 4:
+        m = p3p_four_points(X, x, K64)
+        if m is None:
+            return dict(ok=False, rvec=np.asarray(rvec0, np.float64), tvec=np.asarray(tvec0, np.float64),
+                        inliers=np.zeros(0, np.int32), iters=0)
+        return dict(ok=True, rvec=m[0], tvec=m[1], inliers=np.arange(4, dtype=np.int32), iters=0, model=m)
+    assert n >= 5, "cv::solvePnPRansac needs at least four points"
     rng = CvRNG(MASK64)
     thr = np.float32(np.float64(reproj) * np.float64(reproj))
     niters = iterations

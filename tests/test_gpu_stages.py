@@ -72,14 +72,40 @@ def test_pnp_ransac_masks_and_pose(ctx, n, sigma, outl, seed):
 
 
 def test_pnp_small_counts(ctx):
-    from visual_odom_b200.capi import VoError, VO_E_TOO_FEW_POINTS, VO_E_UNSUPPORTED
+    from visual_odom_b200.capi import VoError, VO_E_TOO_FEW_POINTS
     X, x, K, _ = synth.pnp_stress_set(10, 0.1, 0.0, seed=9)
     with pytest.raises(VoError) as e:
         ctx.pnp_ransac(X[:3], x[:3], K)
     assert e.value.code == VO_E_TOO_FEW_POINTS
-    with pytest.raises(VoError) as e:
-        ctx.pnp_ransac(X[:4], x[:4], K)
-    assert e.value.code == VO_E_UNSUPPORTED
+
+
+def test_pnp_four_points_is_opencvs_p3p_case(ctx):
+    """n == 4 (reference src/visualOdometry.cpp:176-178 with four survivors): cv::solvePnPRansac runs no RANSAC but one P3P
+    solvePnP -- all four points come back as inliers and the pose is the P3P solution the fourth point selects.  Against cv2
+    through the reference glue: inliers identical, [R|t] within 1e-4 absolute (cv2 normalises the image points in f32, which
+    bounds the agreement at ~1e-5)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ref_path
+    rng = np.random.default_rng(5)
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]], np.float32)
+    K64 = K.astype(np.float64)
+    checked = 0
+    for _ in range(60):
+        X = rng.uniform([-8, -2, 5], [8, 2, 40], (4, 3)).astype(np.float32)
+        Rt, _ = cv2.Rodrigues(rng.normal(0, 0.05, 3))
+        tt = rng.normal(0, 0.5, 3)
+        x = (K64 @ (Rt @ X.T.astype(np.float64) + tt[:, None])).T
+        x = (x[:, :2] / x[:, 2:] + rng.normal(0, 0.5, (4, 2))).astype(np.float32)
+        t_prev = np.array([0.02, 0.0, -0.8])
+        P_l = np.zeros((3, 4), np.float32); P_l[:, :3] = K
+        R, t, inl, rvec = ref_path.tracking_frame2frame(P_l, None, x, X, t_prev, backend="cv2")
+        if not np.all(np.isfinite(t)) or len(inl) != 4:
+            continue                                   # cv2's own P3P produced NaN: nothing to compare
+        got = ctx.pnp_ransac(X, x, K, tvec0=t_prev)
+        assert np.array_equal(got["inliers"], np.arange(4)) and got["iters"] == 0
+        assert np.abs(got["R"] - R).max() <= 1e-4 and np.abs(got["tvec"] - np.asarray(t).ravel()).max() <= 1e-4
+        checked += 1
+    assert checked >= 55
 
 
 @pytest.mark.parametrize("n,sigma,outl,seed", [(300, 0.1, 0.1, 0), (500, 0.2, 0.3, 1), (1000, 0.3, 0.5, 2), (200, 0.05, 0.0, 3),

@@ -110,3 +110,66 @@ def test_product_host_math_matches_cv2(built):
     L.vo_hostcheck_triangulate(p(P_l), p(P_r), p(a), p(b), n, p(Xo))
     X4 = cv2.triangulatePoints(P_l, P_r, a.T.copy(), b.T.copy())
     assert np.array_equal(Xo, cv2.convertPointsFromHomogeneous(X4.T.copy()).reshape(-1, 3))
+
+
+def _four_point_sets(count, seed):
+    """Four 3-D points in front of a KITTI-like camera, a small motion, half-pixel noise: the n == 4 input of solvePnPRansac."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]], np.float64)
+    for _ in range(count):
+        X = rng.uniform([-8, -2, 5], [8, 2, 40], (4, 3)).astype(np.float32)
+        R, _ = cv2.Rodrigues(rng.normal(0, 0.05, 3))
+        t = rng.normal(0, 0.5, 3)
+        x = (K @ (R @ X.T.astype(np.float64) + t[:, None])).T
+        x = (x[:, :2] / x[:, 2:] + rng.normal(0, 0.5, (4, 2))).astype(np.float32)
+        yield X, x, K
+
+
+def test_four_point_case_matches_cv2(built):
+    """n == 4: cv::solvePnPRansac runs one P3P solvePnP and reports all four points (reference call site
+    src/visualOdometry.cpp:176-178).  The oracle restatement AND the product's own math (p3p_math.cuh compiled for the
+    host) against cv2: same solution picked, [R|t] within 1e-4 (measured <= 1e-5: cv2 normalises the image points in f32),
+    inliers = 0..3.  The few sets where cv2 itself returns NaN poses are skipped (the library reports "no model" there)."""
+    from visual_odom_b200 import build
+    L = C.CDLL(build.build_hostcheck())
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    checked = 0
+    worst = 0.0
+    for X, x, K in _four_point_sets(600, seed=5):
+        ok, rc, tc, inl = cv2.solvePnPRansac(X, x, K, None, None, None, False, 500, 0.5, 0.999, None, cv2.SOLVEPNP_ITERATIVE)
+        if not ok or not np.all(np.isfinite(tc)):
+            continue
+        assert np.array_equal(inl.ravel(), np.arange(4))
+        Rc, _ = cv2.Rodrigues(rc)
+        got = P.solve_pnp_ransac(X, x, K, np.zeros(3), np.zeros(3))
+        assert got["ok"] and np.array_equal(got["inliers"], np.arange(4)) and got["iters"] == 0
+        Ro = P.rodrigues(got["rvec"])
+        rv = np.zeros(3); tv = np.zeros(3); Rh = np.zeros(9)
+        Kf = np.ascontiguousarray(K, np.float32).ravel()
+        assert L.vo_hostcheck_p3p(p(np.ascontiguousarray(X)), p(np.ascontiguousarray(x)), p(Kf), p(rv), p(tv), p(Rh)) == 1
+        for Rg, tg in ((Ro, got["tvec"]), (Rh.reshape(3, 3), tv)):
+            d = max(np.abs(Rg - Rc).max(), np.abs(tg - tc.ravel()).max())
+            worst = max(worst, d)
+            assert d <= 1e-4, (d, rc.ravel(), tc.ravel())
+        # the two implementations of the same algorithm (numpy's companion-matrix roots vs the product's Durand-Kerner)
+        assert max(np.abs(Ro - Rh.reshape(3, 3)).max(), np.abs(got["tvec"] - tv).max()) <= 1e-4
+        checked += 1
+    assert checked >= 590
+    print(f"four-point case: {checked} sets, worst |d[R|t]| vs cv2 = {worst:.2e}")
+
+
+def test_p3p_solution_set_matches_cv2():
+    """cv::solveP3P's solution set for three points = the restatement's (as sets, 1e-5)."""
+    n_sets = 0
+    for X, x, K in _four_point_sets(200, seed=11):
+        n3, rs, ts = cv2.solveP3P(X[:3], x[:3], K, None, cv2.SOLVEPNP_P3P)
+        if n3 == 0 or not all(np.all(np.isfinite(t)) for t in ts):
+            continue
+        yn = P.undistort_normalize_f32(x[:3], K).astype(np.float64)
+        mine = P.p3p_solutions(X[:3].astype(np.float64), yn)
+        assert len(mine) == n3
+        for r, t in zip(rs, ts):
+            Rc, _ = cv2.Rodrigues(r)
+            assert min(max(np.abs(Rc - R).max(), np.abs(t.ravel() - tt).max()) for R, tt in mine) <= 1e-4
+        n_sets += 1
+    assert n_sets >= 190

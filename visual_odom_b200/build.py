@@ -109,7 +109,7 @@ def build_facade(force=False):
 def build_hostcheck(force=False):
     """pnp_math.cuh compiled for the host (g++), used by the CPU tests to check the kernels' math."""
     src = os.path.join(CSRC, "host_check.cpp")
-    dep = [src, os.path.join(CSRC, "pnp_math.cuh")]
+    dep = [src] + [os.path.join(CSRC, f) for f in ("pnp_math.cuh", "ess_math.cuh", "p3p_math.cuh")]
     if force or _newer(dep, HOSTCHECK_LIB):
         cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src,
                "-o", HOSTCHECK_LIB]

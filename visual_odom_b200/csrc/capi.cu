@@ -180,7 +180,6 @@ extern "C" int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f*
     if (n_inliers) *n_inliers = 0;
     if (n < 0 || !K || !rvec_io || !tvec_io) { vo_set_error(ctx, "bad argument"); return VO_E_INVALID; }
     if (n < 4) { vo_set_error(ctx, "solvePnPRansac needs >= 4 points (got %d); the reference aborts here", n); return VO_E_TOO_FEW_POINTS; }
-    if (n == 4) { vo_set_error(ctx, "n == 4 selects OpenCV's P3P RANSAC kernel, which this library does not build"); return VO_E_UNSUPPORTED; }
     if (n > ctx->cap) { vo_set_error(ctx, "n=%d exceeds max_features=%d", n, ctx->cap); return VO_E_CAPACITY; }
     if (!X || !x) { vo_set_error(ctx, "null argument"); return VO_E_INVALID; }
     if (rvec_io[0] != 0 || rvec_io[1] != 0 || rvec_io[2] != 0) {

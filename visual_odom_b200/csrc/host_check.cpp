@@ -3,6 +3,7 @@
 // It is a test hook of the product's own math, not a fallback: nothing in the library calls it.
 #include "pnp_math.cuh"
 #include "ess_math.cuh"
+#include "p3p_math.cuh"
 #include <vector>
 extern "C" {
 __attribute__((visibility("default"))) void vo_hostcheck_epnp5(const float* X, const float* uv, const float* K9, double* rvec, double* tvec, double* R)
@@ -19,6 +20,15 @@ __attribute__((visibility("default"))) void vo_hostcheck_rodrigues(const double*
 {
     vomath::rodrigues_fwd(r, R);
     vomath::rodrigues_inv(R, r_back);
+}
+// the n == 4 case of solvePnPRansac as k_pnp_finalize runs it: returns 1 and (rvec, tvec, R = Rodrigues(rvec)) or 0
+__attribute__((visibility("default"))) int vo_hostcheck_p3p(const float* X4, const float* uv4, const float* K9, double* rvec, double* tvec, double* R)
+{
+    double Rp[9];
+    if (!vomath::p3p_four_points(X4, uv4, (double)K9[0], (double)K9[4], (double)K9[2], (double)K9[5], Rp, tvec)) return 0;
+    vomath::rodrigues_inv(Rp, rvec);
+    vomath::rodrigues_fwd(rvec, R);
+    return 1;
 }
 __attribute__((visibility("default"))) int vo_hostcheck_five_point(const double* q1, const double* q2, double* E_out)
 {

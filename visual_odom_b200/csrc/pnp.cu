@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "pnp.h"
 #include "pnp_math.cuh"
+#include "p3p_math.cuh"
 
 using namespace vomath;
 
@@ -50,7 +51,7 @@ __global__ void k_pnp_init(const PnpArgs a)
     s.best_it = -1;
     s.iters_run = 0;
     const int n = a.n_pts[unit];
-    s.done = (n < 5) ? 1 : 0;           // n < 4: the reference aborts; n == 4: P3P kernel (not built)
+    s.done = (n < 5) ? 1 : 0;           // n < 4: the reference aborts; n == 4: no RANSAC, k_pnp_finalize runs the P3P solve
 }
 
 __global__ void k_pnp_subsets(const PnpArgs a, int it0, int it1)
@@ -382,12 +383,40 @@ __global__ void __launch_bounds__(FIN_T) k_pnp_finalize(const PnpArgs a)
     __shared__ double shared_norm;
 
     const double* t_prev = a.t_prev + 3 * unit;
+    if (n == 4) {
+        // exactly four correspondences: OpenCV runs no RANSAC, one P3P solvePnP on all four, no refinement, all four inliers
+        if (threadIdx.x == 0) {
+            float Xw[12], uv[8];
+            for (int i = 0; i < 4; i++) {
+                Xw[3 * i] = X[i].x; Xw[3 * i + 1] = X[i].y; Xw[3 * i + 2] = X[i].z;
+                uv[2 * i] = x[i].x; uv[2 * i + 1] = x[i].y;
+            }
+            double R[9], t[3], rv[3];
+            const bool ok = p3p_four_points(Xw, uv, a.fu, a.fv, a.uc, a.vc, R, t);
+            res.ransac_iters = 0;
+            if (ok) {
+                rodrigues_inv(R, rv);
+                rodrigues_fwd(rv, R);                  // the caller's cv::Rodrigues(rvec, rotation), visualOdometry.cpp:180
+                res.n_inliers = 4;
+                res.pnp_status = VO_PNP_OK;
+                for (int i = 0; i < 4; i++) inl[i] = i;
+                for (int k = 0; k < 3; k++) { res.rvec[k] = rv[k]; res.tvec[k] = t[k]; }
+                for (int k = 0; k < 9; k++) res.R[k] = R[k];
+            } else {
+                res.n_inliers = 0;
+                res.pnp_status = VO_PNP_NO_MODEL;
+                for (int k = 0; k < 3; k++) { res.rvec[k] = 0; res.tvec[k] = t_prev[k]; }
+                for (int k = 0; k < 9; k++) res.R[k] = (k % 4 == 0) ? 1. : 0.;
+            }
+        }
+        return;
+    }
     if (st.best_it < 0 || n < 5) {
         // solvePnPRansac returns false: rvec / tvec stay what the caller passed in
         if (threadIdx.x == 0) {
             res.n_inliers = 0;
             res.ransac_iters = st.iters_run;
-            res.pnp_status = (n < 4) ? VO_PNP_TOO_FEW : (n == 4 ? VO_PNP_UNSUPPORTED_P3P : VO_PNP_NO_MODEL);
+            res.pnp_status = (n < 4) ? VO_PNP_TOO_FEW : VO_PNP_NO_MODEL;
             for (int k = 0; k < 3; k++) { res.rvec[k] = 0; res.tvec[k] = t_prev[k]; }
             for (int k = 0; k < 9; k++) res.R[k] = (k % 4 == 0) ? 1. : 0.;
         }

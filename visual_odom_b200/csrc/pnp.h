@@ -4,7 +4,6 @@
 
 #define VO_PNP_OK 0
 #define VO_PNP_TOO_FEW (-3)            // n < 4: the reference would abort inside cv::solvePnPRansac
-#define VO_PNP_UNSUPPORTED_P3P (-4)    // n == 4: OpenCV switches to a P3P kernel, not built here
 #define VO_PNP_NO_MODEL 1              // RANSAC found no model with > 4 inliers: pose = caller's guess
 
 struct PnpState {
