@@ -220,9 +220,12 @@ def cpu_reference_measure(units, args, seconds_per_mode=10.0, reps=3):
             pool.map(_pool_run, [1] * (2 * n_proc), chunksize=1)          # every worker initialised and warm
             curve = {}
             for k in sorted({max(1, n_proc // 4), max(1, n_proc // 2), n_proc}):
-                t0 = time.perf_counter()
-                done = sum(pool.map(_pool_run, [2] * k, chunksize=1))     # k tasks -> k busy workers
-                curve[k] = done / (time.perf_counter() - t0)
+                best = 0.0
+                for _ in range(2):                                            # best of two: the first pass can still see workers finishing their initialiser
+                    t0 = time.perf_counter()
+                    done = sum(pool.map(_pool_run, [2] * k, chunksize=1))     # k tasks -> k busy workers
+                    best = max(best, done / (time.perf_counter() - t0))
+                curve[k] = best
             k_best = max(curve, key=curve.get)
             chunk = max(2, int(np.ceil(curve[k_best] * seconds_per_mode / reps / k_best)))
             fps = []
@@ -546,9 +549,11 @@ class Point:
 
 
 class NativeGather:
-    """Record gather through the library's own C-ABI (vo_dist_*: ncclAllGather straight from the device records of the
-    waited submission, one D2H into pinned memory, nothing blocks until two gathers are outstanding)."""
-    kind = "C-ABI vo_dist_gather_post / vo_dist_gather_wait (NCCL resolved with dlopen inside libvo_b200.so)"
+    """Record gather through the library's own C-ABI (vo_dist_*: device snapshot of the waited submission's records, in-place
+    ncclAllGather, one D2H into pinned memory; nothing blocks until VO_DIST_DEPTH gathers are outstanding, and a submission
+    that refills the slots never waits for another rank)."""
+    kind = "C-ABI vo_dist_gather_post / vo_dist_gather_wait (NCCL resolved with dlopen inside libvo_b200.so), 8 gathers in flight"
+    DEPTH = 8                                   # VO_DIST_DEPTH, include/vo_b200.h
 
     def __init__(self, ctx, B):
         self.ctx, self.B, self.outstanding, self.tables = ctx, B, 0, []
@@ -558,7 +563,7 @@ class NativeGather:
         self.outstanding -= 1
 
     def post_step(self, slot, out, my_units):
-        if self.outstanding == 2:
+        if self.outstanding == self.DEPTH:
             self._harvest()
         self.ctx.dist_gather_post(slot, self.B)
         self.outstanding += 1
@@ -583,6 +588,29 @@ class TorchGather:
 
     def drain(self):
         return self.g.drain()
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Multi-rank runs: keep this rank's host threads -- and therefore the pinned staging it allocates next, which the kernel
+    places on the allocating thread's node -- on the NUMA node its GPU hangs off, so the per-step H2D / D2H copies do not cross
+    the socket interconnect.  Pure host plumbing (sysfs + sched_setaffinity); returns what was done for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"node": None, "why": "sysfs reports no NUMA node for " + bdf}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:
+        return {"node": None, "why": str(e)[:100]}
 
 
 def lk_profile_constants():
@@ -615,6 +643,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this library has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 and os.environ.get("VO_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -656,7 +685,7 @@ def main():
         torch.cuda.synchronize()
 
     gather = None
-    if world > 1:
+    if world > 1 and os.environ.get("VO_BENCH_GATHER", "1") != "0":       # =0: diagnostic only (how much the collective costs)
         try:                               # NCCL unique id: made by rank 0 inside the library, broadcast out of band
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -769,7 +798,9 @@ def main():
                             "(4 images per unit from pinned host memory), kernels, and D2H of the result records AND of every unit's point "
                             "lists (4 x n_valid points, tracked-feature indices, points3D, inlier list: one packed copy per submission) "
                             "are inside the timed region" + ("; the NCCL all-gather of the records runs non-blocking on a side stream and "
-                                                             "is drained inside the timed region (" + gather.kind + ")" if world > 1 else ""),
+                                                             "is drained inside the timed region (" + gather.kind + ")" if gather is not None else
+                                                            ("; record gather DISABLED by VO_BENCH_GATHER=0 (diagnostic run)" if world > 1 else "")),
+                    "host_numa_binding": numa,
                     "summary_only": {"value": frames / (ms_sum * 1e-3), "d2h_bytes_per_step": d2h_records,
                                      "note": "round-1 definition: result records only"},
                     "equals_resident_results": all(a["n_inliers"] == b["n_inliers"] and np.array_equal(a["tvec"], b["tvec"])

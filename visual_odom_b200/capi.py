@@ -17,6 +17,7 @@ VO_E_INVALID = -1
 VO_E_CUDA = -2
 VO_E_TOO_FEW_POINTS = -3
 VO_E_UNSUPPORTED = -4
+VO_DIST_DEPTH = 8          # gathers that may be outstanding (include/vo_b200.h)
 VO_E_CAPACITY = -5
 
 

@@ -98,12 +98,14 @@ struct vo_ctx {
     void* dist_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
     cudaStream_t dist_stream = nullptr;
-    cudaEvent_t dist_ev_read[2] = {nullptr, nullptr}, dist_ev_done[2] = {nullptr, nullptr}, dist_ev_fork = nullptr;
-    void* d_dist[2] = {nullptr, nullptr};
-    void* h_dist[2] = {nullptr, nullptr};
+    // a ring of VO_DIST_DEPTH gathers in flight: entry k owns a device table (this rank's records are snapshotted into their
+    // place in it, then gathered in place), a pinned host table and two events
+    cudaEvent_t dist_ev_read[VO_DIST_DEPTH] = {}, dist_ev_done[VO_DIST_DEPTH] = {}, dist_ev_fork = nullptr;
+    void* d_dist[VO_DIST_DEPTH] = {};
+    void* h_dist[VO_DIST_DEPTH] = {};
     size_t dist_bytes = 0;
-    bool dist_posted[2] = {false, false};
-    int dist_n[2] = {0, 0};
+    bool dist_posted[VO_DIST_DEPTH] = {};
+    int dist_n[VO_DIST_DEPTH] = {};
     long long dist_head = 0, dist_tail = 0;
     // mono_rotation branch (ess.cu): scratch of the essential-matrix RANSAC, allocated on first use
     void* d_ess = nullptr;
