@@ -156,3 +156,42 @@ def test_full_size_properties_static_camera_and_determinism(ctx):
         assert np.array_equal(a["rvec"], b["rvec"]) and np.array_equal(a["tvec"], b["tvec"])
         for key in ("kept_idx", "l0", "r0", "l1", "r1", "X", "inliers"):
             assert np.array_equal(ga[key], gb[key]), key
+
+
+def test_record_gather_ring_world_of_one(built):
+    """SURVEY.md 8(e), the C-ABI record gather (vo_dist_*), on one GPU as a world of one rank: a posted gather returns the
+    records AS THEY WERE WHEN POSTED even though the slots are refilled right away (the device snapshot is what decouples a
+    submission from the other ranks), VO_DIST_DEPTH posts may be outstanding, and one more is refused."""
+    import torch                                         # makes libnccl.so.2 resident for the library's dlopen
+    from visual_odom_b200.capi import Context, VO_DIST_DEPTH
+    w, h, B = 640, 240, 2
+    c = Context(0, max_features=2048, max_units=2 * B)
+    try:
+        try:
+            uid = c.dist_unique_id()
+        except RuntimeError:
+            pytest.skip("no loadable NCCL on this host")
+        c.dist_init(uid, 0, 1)
+        sets = [[synth.stereo_unit(w, h, 7 * k + s) for s in range(B)] for k in range(VO_DIST_DEPTH)]
+        c.batch_configure(w, h, 2 * B, sets[0][0]["P_l"], sets[0][0]["P_r"])
+        arrs = [c.make_units([dict(u, n_select=300, t_prev=(0, 0, -0.8)) for u in us]) for us in sets]
+        expect = []
+        for k in range(VO_DIST_DEPTH):                    # every step reuses slot range (k % 2) * B: the gather must not see the refill
+            s0 = (k % 2) * B
+            c.batch_submit(arrs[k][0], s0, arrs[k][2])
+            res = c.batch_wait(s0, B)
+            c.dist_gather_post(s0, B)
+            expect.append(res)
+        with pytest.raises(RuntimeError, match="outstanding"):
+            c.dist_gather_post(0, B)
+        assert len({tuple(r["tvec"]) for res in expect for r in res}) == VO_DIST_DEPTH * B      # the steps really differ
+        for k in range(VO_DIST_DEPTH):
+            got = c.dist_gather_wait(B)
+            assert len(got) == B
+            for a, b in zip(got, expect[k]):
+                assert a["n_inliers"] == b["n_inliers"] and a["n_valid"] == b["n_valid"]
+                assert np.array_equal(a["tvec"], b["tvec"]) and np.array_equal(a["R"], b["R"])
+        with pytest.raises(RuntimeError, match="nothing outstanding"):
+            c.dist_gather_wait(B)
+    finally:
+        c.close()
