@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W_IMG, H_IMG, N_FEAT = 1241, 376, 2000
+E2E_DEPTH = int(os.environ.get("VO_BENCH_DEPTH", "3"))     # submissions in flight on the end-to-end path (the library has 3 lanes)
 LK_BYTES_PER_FEATURE = 4 * (4 * ((21 + 3) ** 2 + (21 + 1) ** 2) + 21)      # 17044, SURVEY.md 8(d)
 METRIC = "stereo frames/sec at 1241x376, 2000 feats; LK kernel HBM GB/s vs roofline"
 
@@ -439,12 +440,13 @@ class Point:
     def __init__(self, ctx, torch, stream, flush, pinned, feats, B, w, h, P_l, P_r, barrier, world, gather=None, my_units=None):
         self.ctx, self.torch, self.stream, self.flush, self.B, self.feats = ctx, torch, stream, flush, B, feats
         self.w, self.h, self.barrier, self.world, self.gather, self.my_units = w, h, barrier, world, gather, my_units
-        ctx.batch_configure(w, h, 2 * B, P_l, P_r)                  # two slot ranges of B (two submissions in flight)
+        self.depth = E2E_DEPTH
+        ctx.batch_configure(w, h, self.depth * B, P_l, P_r)         # slot ranges of B units: `depth` submissions in flight end to end, two resident
         spec = [dict(p, n_select=feats, t_prev=(0.0, 0.0, -0.8)) for p in pinned]
         self.arr, self.keep, self.pitch = ctx.make_units(spec)
         self.arr2, self.keep2, _ = ctx.make_units(spec + spec)
         self.into = [[dict(pts4=np.zeros((4, feats, 2), np.float32), kept_idx=np.zeros(feats, np.int32),
-                           X=np.zeros((feats, 3), np.float32), inliers=np.zeros(feats, np.int32)) for _ in range(B)] for _ in range(2)]
+                           X=np.zeros((feats, 3), np.float32), inliers=np.zeros(feats, np.int32)) for _ in range(B)] for _ in range(self.depth)]
         self.last_outputs = None
         self.d2h_outputs = 0
 
@@ -518,14 +520,16 @@ class Point:
         out = None
         if ev:
             ev[0].record(self.stream)
-        ctx.batch_submit(self.arr, 0, self.pitch)
+        D = self.depth                                         # submissions in flight: the upload of step s + D - 1 is queued
+        for k in range(min(D - 1, n)):                         # before the host waits for step s, so neither the host's enqueue
+            ctx.batch_submit(self.arr, (k % D) * B, self.pitch)  # time nor the H2D copy sits between two steps of the GPU
         for s in range(n):
-            if s + 1 < n:
-                ctx.batch_submit(self.arr, ((s + 1) & 1) * B, self.pitch)
-            slot = (s & 1) * B
+            if s + D - 1 < n:
+                ctx.batch_submit(self.arr, ((s + D - 1) % D) * B, self.pitch)
+            slot = (s % D) * B
             out = ctx.batch_wait(slot, B)
             if self.full_outputs:                              # what matchingFeatures / trackingFrame2Frame hand back
-                self.last_outputs = [ctx.batch_outputs(slot + u, out[u], into=self.into[s & 1][u]) for u in range(B)]
+                self.last_outputs = [ctx.batch_outputs(slot + u, out[u], into=self.into[s % D][u]) for u in range(B)]
             if self.gather is not None:                        # result gather: fixed-size records over NCCL, non-blocking
                 self.gather.post_step(slot, out, self.my_units)
         if self.gather is not None:
@@ -549,10 +553,10 @@ class Point:
 
 
 class NativeGather:
-    """Record gather through the library's own C-ABI (vo_dist_*: device snapshot of the waited submission's records, in-place
-    ncclAllGather, one D2H into pinned memory; nothing blocks until VO_DIST_DEPTH gathers are outstanding, and a submission
-    that refills the slots never waits for another rank)."""
-    kind = "C-ABI vo_dist_gather_post / vo_dist_gather_wait (NCCL resolved with dlopen inside libvo_b200.so), 8 gathers in flight"
+    """Record gather through the library's own C-ABI (vo_dist_*: every step posts a device snapshot of the waited submission's
+    records; one in-place ncclAllGather + one D2H into pinned memory per 4 posts; nothing blocks until VO_DIST_DEPTH posts are
+    outstanding, and a submission that refills the slots never waits for another rank)."""
+    kind = "C-ABI vo_dist_gather_post / vo_dist_gather_wait (NCCL resolved with dlopen inside libvo_b200.so): per-step device snapshot, one all-gather per 4 steps, up to 8 posts outstanding"
     DEPTH = 8                                   # VO_DIST_DEPTH, include/vo_b200.h
 
     def __init__(self, ctx, B):
@@ -670,7 +674,7 @@ def main():
         return out
 
     pinned = pin_units(units, W_IMG, H_IMG)
-    ctx = Context(local_rank, max_features=max(2048, args.features), max_units=2 * B)
+    ctx = Context(local_rank, max_features=max(2048, args.features), max_units=E2E_DEPTH * B)
     stream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -752,7 +756,7 @@ def main():
         if world == 1 and args.sweep:
             try:
                 ctx.close()
-                ctx = Context(local_rank, max_features=8192, max_units=2 * B)
+                ctx = Context(local_rank, max_features=8192, max_units=E2E_DEPTH * B)
                 ctx.set_stream(stream.cuda_stream)
 
                 def run_point(us_pinned, feats, b, w, h, Pm, steps=10):
@@ -794,7 +798,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * 4 * W_IMG * H_IMG + B * 32,
                     "d2h_bytes_per_step": d2h_records + pt.d2h_outputs, "ms_per_step": t_e2e_ms / args.steps,
                     "wall_ms_per_step": 1e3 * _median(wall_e2e) / args.steps,
-                    "mode": "vo_batch_submit / vo_batch_wait / vo_batch_outputs, two submissions of units_per_gpu in flight; every step's H2D "
+                    "mode": f"vo_batch_submit / vo_batch_wait / vo_batch_outputs, {E2E_DEPTH} submissions of units_per_gpu in flight; every step's H2D "
                             "(4 images per unit from pinned host memory), kernels, and D2H of the result records AND of every unit's point "
                             "lists (4 x n_valid points, tracked-feature indices, points3D, inlier list: one packed copy per submission) "
                             "are inside the timed region" + ("; the NCCL all-gather of the records runs non-blocking on a side stream and "

@@ -208,12 +208,13 @@ VO_API int vo_batch_fetch(vo_ctx* ctx, int unit, vo_point2f* pts_in, vo_point2f*
 /* ---- multi-GPU: gather of the result records over NCCL (one process per GPU, units sharded) -----------
  * The path has no data-path collective; the only exchange is the gather of the fixed-size records.  NCCL is resolved with
  * dlopen at vo_dist_init (VO_E_UNSUPPORTED when the host has none).  Rank 0 makes the id with vo_dist_unique_id and hands the
- * 128 bytes to the other ranks out of band; every rank calls vo_dist_init once.  vo_dist_gather_post enqueues, without
- * blocking, an ncclAllGather of the records of resident slots [first_unit, first_unit + n_units) (same n_units on every
- * rank) plus one copy into pinned staging.  The slots' records are first snapshotted on the device, so the slots may be
- * refilled at once: a later submission never waits for another rank.  Up to VO_DIST_DEPTH posts may be outstanding (ranks
- * drift apart by that many steps before anyone blocks); vo_dist_gather_wait returns the oldest one:
- * all[r * n_units + i] = record i of rank r. */
+ * 128 bytes to the other ranks out of band; every rank calls vo_dist_init once.  vo_dist_gather_post posts, without
+ * blocking, the records of resident slots [first_unit, first_unit + n_units) (same n_units on every rank): the post is a
+ * device-side snapshot, so the slots may be refilled at once and a later submission never waits for another rank.  The
+ * exchange itself is batched: one in-place ncclAllGather + one copy into pinned staging per 4 posts, or as soon as
+ * vo_dist_gather_wait needs a posted step that has not been exchanged yet.  Up to VO_DIST_DEPTH posts may be outstanding
+ * (ranks may drift apart by that many steps before anyone blocks); vo_dist_gather_wait returns the oldest one:
+ * all[r * n_units + i] = record i of rank r.  Every rank must post and wait in the same order. */
 #define VO_DIST_DEPTH 8
 VO_API int vo_dist_unique_id(uint8_t id_out[128]);
 VO_API int vo_dist_init(vo_ctx* ctx, const uint8_t id[128], int rank, int world);

@@ -1,5 +1,15 @@
 cd $GRAFT_REPO_ROOT
-( time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_r2e_n8.json 2> gpurun_out/bench_r2e_n8.err ) 2>&1 | grep real
-tail -c 300 gpurun_out/bench_r2e_n8.err; tail -1 gpurun_out/bench_r2e_n8.json | head -c 200; echo
-( time VO_BENCH_GATHER=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/bench_r2e_n8_nogather.json 2> gpurun_out/bench_r2e_n8_nogather.err ) 2>&1 | grep real
-tail -1 gpurun_out/bench_r2e_n8_nogather.json | head -c 200; echo
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+run() { name=$1; n=$2; shift 2; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $n --steps 20 --warmup 3 --sweep 0 --cpu-seconds 0.3 > gpurun_out/diag_$name.json 2> gpurun_out/diag_$name.err
+  python - "$name" <<'PY'
+import json,sys
+n=sys.argv[1]
+try:
+    d=json.loads(open(f'gpurun_out/diag_{n}.json').read().strip().splitlines()[-1]); e=d['e2e']
+    print(n, 'value',round(d['value']),'e2e',round(e['value']),'summary',round(e['summary_only']['value']),'blocks',d['timed_blocks_ms']['e2e'], d['parity']['vs_oracle'], d['parity']['gathered_records_ok_rank0'])
+except Exception as ex: print(n,'failed',ex); print(open(f'gpurun_out/diag_{n}.err').read()[-600:])
+PY
+}
+run bk_n2 2 A=1
+run bk_n2_nogather 2 VO_BENCH_GATHER=0
+run bk_n2_b 2 A=1

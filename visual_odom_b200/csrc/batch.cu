@@ -156,7 +156,7 @@ static int ensure_side_streams(vo_ctx* ctx)
 {
     if (ctx->fork_ev) return VO_OK;
     VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < VO_LANES; c++) {
         VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side_stream[c], cudaStreamNonBlocking));
         VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->join_ev[c], cudaEventDisableTiming));
     }
@@ -172,7 +172,7 @@ static int ensure_hi_streams(vo_ctx* ctx)
     if (ctx->hi_stream[0]) return VO_OK;
     int lo = 0, hi = 0;
     VO_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi is the numerically smallest value
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < VO_LANES; c++) {
         VO_CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->hi_stream[c], cudaStreamNonBlocking, hi));
         for (int k = 0; k < 4; k++) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->hi_ev[c][k], cudaEventDisableTiming));
     }
@@ -186,7 +186,7 @@ static int run_range_launch(vo_ctx* ctx, const View& v)
     ctx->imgs_per_unit = 4;
     int rc;
     int c = -1;
-    for (int k = 0; k < 2; k++) if (ctx->side_stream[k] && v.s == ctx->side_stream[k]) c = k;
+    for (int k = 0; k < VO_LANES; k++) if (ctx->side_stream[k] && v.s == ctx->side_stream[k]) c = k;
     // With the SM partition on, a side-stream range runs its LK ring on the LK partition's stream and everything else on the
     // helper partition's stream; otherwise (priorities) everything but the LK ring goes to the side stream's high-priority helper.
     const bool part = ctx->part_on && c >= 0;
@@ -249,7 +249,7 @@ static int run_range(vo_ctx* ctx, const View& v)
     // priority split is worth more (+7 % on the pipelined step) than the graph's launch savings (+2 %): ranges that run
     // on a side stream with priorities enabled are launched plainly unless "batch_graphs" forces graphs.
     bool on_side = false;
-    for (int k = 0; k < 2; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
+    for (int k = 0; k < VO_LANES; k++) on_side = on_side || (ctx->side_stream[k] && v.s == ctx->side_stream[k]);
     if (!ctx->use_graphs || ((ctx->use_priorities || ctx->part_on) && on_side && !ctx->batch_graphs)) return run_range_launch(ctx, v);
     for (auto& g : ctx->graphs)
         if (g.u0 == v.u0 && g.n == v.n && g.detect == ctx->batch_detect && g.tma == ctx->lk_use_tma && g.s == v.s && g.max_pts == ctx->batch_max_pts) {
@@ -406,7 +406,7 @@ extern "C" int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit
         slot = &ctx->pending.back();
         VO_CUDA_CHECK(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
     }
-    const int c = (ctx->submit_count++) & 1;
+    const int c = (int)((ctx->submit_count++) % VO_LANES);     // up to VO_LANES submissions in flight, each on its own lane
     cudaStream_t st = ctx->side_stream[c];
     VO_CUDA_CHECK(cudaEventRecord(ctx->fork_ev, ctx->stream));
     VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->fork_ev, 0));

@@ -92,7 +92,7 @@ extern "C" void vo_destroy(vo_ctx* ctx)
         if (ctx->seq_back_ev[k]) cudaEventDestroy(ctx->seq_back_ev[k]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < VO_LANES; c++) {
         if (ctx->join_ev[c]) cudaEventDestroy(ctx->join_ev[c]);
         if (ctx->side_stream[c]) cudaStreamDestroy(ctx->side_stream[c]);
         if (ctx->hi_stream[c]) cudaStreamDestroy(ctx->hi_stream[c]);
@@ -211,7 +211,7 @@ static bool drv(const char* name, F* fn)
 
 void vo_partition_destroy(vo_ctx* ctx)
 {
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < VO_LANES; c++) {
         if (ctx->part_lk_stream[c]) cudaStreamDestroy(ctx->part_lk_stream[c]);
         if (ctx->part_hp_stream[c]) cudaStreamDestroy(ctx->part_hp_stream[c]);
         ctx->part_lk_stream[c] = ctx->part_hp_stream[c] = nullptr;
@@ -261,7 +261,7 @@ int vo_partition_enable(vo_ctx* ctx, int helper_sms)
         ctx->part_gctx[k] = g;
     }
     ctx->part_helper_sms = (int)part[0].sm.smCount; ctx->part_lk_sms = (int)rest.sm.smCount;
-    for (int c = 0; c < 2; c++) {
+    for (int c = 0; c < VO_LANES; c++) {
         CUstream a, b;
         if ((r = screate(&a, (CUgreenCtx)ctx->part_gctx[0], CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS ||
             (r = screate(&b, (CUgreenCtx)ctx->part_gctx[1], CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
@@ -545,14 +545,14 @@ int vo_run_lk_ring(vo_ctx* ctx, const View& v, int ncalls, const int* img_prev, 
         a.progress = ctx->d_lk_progress + uo;
         {   // a launch with fewer features than resident warps gains nothing from splitting its rings
             int lk_sms = ctx->sm_count;
-            for (int c = 0; c < 2; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
+            for (int c = 0; c < VO_LANES; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
             const long resident_warps = (long)lk_sms * vo_lk_ctas_per_sm(ctx->lk_ctas_per_sm) * LK_WARPS_PER_CTA;
             const bool big = (long)a.n_units * a.per_unit > resident_warps;
             a.span = ctx->lk_span > 0 ? ctx->lk_span : (big ? 2 : 0);
             a.quota = big ? ctx->lk_quota : 0;
         }
         int lk_sms = ctx->sm_count;
-        for (int c = 0; c < 2; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
+        for (int c = 0; c < VO_LANES; c++) if (ctx->part_on && v.s == ctx->part_lk_stream[c]) lk_sms = ctx->part_lk_sms;
         VO_CUDA_CHECK(vo_launch_lk_ring(ctx->maps, a, lk_sms, ctx->lk_ctas_per_sm, v.s));
     }
     ctx->launches += 1;

@@ -11,6 +11,9 @@
 #include <vector>
 #include <stdarg.h>
 #define LK_QUEUES 32
+#define VO_DIST_BUCKET 4       // posted steps per collective
+#define VO_DIST_NB 4           // buckets (ring)
+#define VO_LANES 3            // submissions in flight, each with its own side stream / partition streams / events
 
 struct vo_ctx {
     int device = 0;
@@ -91,21 +94,23 @@ struct vo_ctx {
                                         // kernels after the ring (filters, triangulation, PnP) go to the small one
     int part_helper_sms = 0, part_lk_sms = 0;
     void* part_gctx[2] = {nullptr, nullptr};            // CUgreenCtx: [0] helpers, [1] LK
-    cudaStream_t part_lk_stream[2] = {nullptr, nullptr};     // per side stream
-    cudaStream_t part_hp_stream[2] = {nullptr, nullptr};
-    cudaEvent_t part_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    cudaStream_t part_lk_stream[VO_LANES] = {};     // per side stream
+    cudaStream_t part_hp_stream[VO_LANES] = {};
+    cudaEvent_t part_ev[VO_LANES][4] = {};
     // multi-GPU record gather over NCCL (dist.cu); NCCL is dlopen'ed at vo_dist_init
     void* dist_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
     cudaStream_t dist_stream = nullptr;
-    // a ring of VO_DIST_DEPTH gathers in flight: entry k owns a device table (this rank's records are snapshotted into their
-    // place in it, then gathered in place), a pinned host table and two events
-    cudaEvent_t dist_ev_read[VO_DIST_DEPTH] = {}, dist_ev_done[VO_DIST_DEPTH] = {}, dist_ev_fork = nullptr;
-    void* d_dist[VO_DIST_DEPTH] = {};
-    void* h_dist[VO_DIST_DEPTH] = {};
+    // up to VO_DIST_DEPTH posted steps outstanding.  A post only snapshots the records (device to device) into the open
+    // bucket; a bucket is exchanged with ONE in-place all-gather + ONE copy to pinned memory when it holds VO_DIST_BUCKET
+    // steps, or earlier when the host asks for one of its steps.
+    struct DistBucket { void* d = nullptr; void* h = nullptr; cudaEvent_t done = nullptr; int fill = 0, unwaited = 0, n_units = 0; bool flushed = false; };
+    struct DistStep { int bucket = 0, index = 0; };
+    DistBucket dist_bk[VO_DIST_NB];
+    DistStep dist_steps[2 * VO_DIST_DEPTH];
+    int dist_cur = 0;
+    cudaEvent_t dist_ev_read = nullptr, dist_ev_fork = nullptr;
     size_t dist_bytes = 0;
-    bool dist_posted[VO_DIST_DEPTH] = {};
-    int dist_n[VO_DIST_DEPTH] = {};
     long long dist_head = 0, dist_tail = 0;
     // mono_rotation branch (ess.cu): scratch of the essential-matrix RANSAC, allocated on first use
     void* d_ess = nullptr;
@@ -144,12 +149,12 @@ struct vo_ctx {
     struct RangeGraph { int u0, n; bool detect, tma; cudaStream_t s; int max_pts; cudaGraphExec_t exec; long long launches; };   // s: the stream it was captured on (its LK work queue is that stream's)
     std::vector<RangeGraph> graphs; // invalidated when the device state is re-allocated
     int batch_max_pts = 0;          // largest per-unit feature count of the resident batch
-    cudaStream_t hi_stream[2] = {nullptr, nullptr};     // high-priority helpers of the side streams (see run_range_launch)
-    cudaEvent_t hi_ev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    cudaStream_t hi_stream[VO_LANES] = {};     // high-priority helpers of the side streams (see run_range_launch)
+    cudaEvent_t hi_ev[VO_LANES][4] = {};
     bool use_priorities = true;
     bool batch_graphs = false;      // force CUDA graphs for side-stream ranges even though they lose the priority split
-    cudaStream_t side_stream[2] = {nullptr, nullptr};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k)
-    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+    cudaStream_t side_stream[VO_LANES] = {};   // pipelining of vo_frame_batch (H2D of chunk k+1 under compute of chunk k) and of vo_batch_submit
+    cudaEvent_t fork_ev = nullptr, join_ev[VO_LANES] = {};
     struct Pending { int u0 = 0, n = 0; bool active = false; cudaEvent_t done = nullptr; };
     std::vector<Pending> pending;   // vo_batch_submit / vo_batch_wait
     // full outputs of a submission (what matchingFeatures / trackingFrame2Frame hand back): packed per unit on the

@@ -3,8 +3,8 @@
 //
 //   rank 0: vo_dist_unique_id(id)  ->  the 128 bytes travel out of band (bench.py broadcasts them with torch.distributed)
 //   all   : vo_dist_init(ctx, id, rank, world)
-//   loop  : vo_batch_wait(slot) ; vo_dist_gather_post(ctx, slot, n)      non-blocking: ncclAllGather straight from the device
-//           ...                 ; vo_dist_gather_wait(ctx, all, ...)     snapshot of the submission's records, + one D2H into pinned memory
+//   loop  : vo_batch_wait(slot) ; vo_dist_gather_post(ctx, slot, n)      non-blocking: device snapshot of the records into a bucket;
+//           ...                 ; vo_dist_gather_wait(ctx, all, ...)     one in-place ncclAllGather + one D2H per 4 posts
 // NCCL is resolved with dlopen at vo_dist_init, so libvo_b200.so itself does not link it (the library must load on hosts
 // without NCCL, e.g. the CPU test box); the process-wide libnccl.so.2 that torch already loaded is the one that is found.
 #include "ctx.h"
@@ -59,42 +59,66 @@ extern "C" int vo_dist_init(vo_ctx* ctx, const uint8_t id[128], int rank, int wo
     if (!id || world < 1 || rank < 0 || rank >= world) { vo_set_error(ctx, "vo_dist_init: bad argument"); return VO_E_INVALID; }
     if (const char* e = load_nccl()) { vo_set_error(ctx, "vo_dist_init: %s", e); return VO_E_UNSUPPORTED; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    if (ctx->dist_comm) { g_nccl.CommDestroy((NcclComm)ctx->dist_comm); ctx->dist_comm = nullptr; }
+    if (ctx->dist_comm) vo_dist_shutdown(ctx);
     NcclUid uid;
     memcpy(uid.internal, id, 128);
     NcclComm comm = nullptr;
     const int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
     if (rc != 0) { vo_set_error(ctx, "ncclCommInitRank: %s", nccl_err(rc)); return VO_E_CUDA; }
     ctx->dist_comm = comm; ctx->dist_rank = rank; ctx->dist_world = world;
-    if (!ctx->dist_stream) VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->dist_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < VO_DIST_DEPTH; k++) {
-        if (!ctx->dist_ev_read[k]) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_read[k], cudaEventDisableTiming));
-        if (!ctx->dist_ev_done[k]) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_done[k], cudaEventDisableTiming));
-        ctx->dist_posted[k] = false;
+    VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->dist_stream, cudaStreamNonBlocking));
+    VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_read, cudaEventDisableTiming));
+    VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_fork, cudaEventDisableTiming));
+    for (auto& bk : ctx->dist_bk) {
+        VO_CUDA_CHECK(cudaEventCreateWithFlags(&bk.done, cudaEventDisableTiming));
+        bk.fill = bk.unwaited = bk.n_units = 0; bk.flushed = false;
     }
+    ctx->dist_cur = 0;
     ctx->dist_head = ctx->dist_tail = 0;
+    ctx->dist_bytes = 0;
     return VO_OK;
 }
 
-static int dist_buffers(vo_ctx* ctx, int n_units)
+// a bucket's table: [rank][VO_DIST_BUCKET][units of the state] records, device + pinned host; sized for the whole state, so
+// it is (re)allocated only when the state grows, which needs every post handed out first
+static int dist_buffers(vo_ctx* ctx)
 {
-    const size_t need = (size_t)ctx->dist_world * n_units * sizeof(vo_unit_result_dev);
+    const size_t need = (size_t)ctx->dist_world * VO_DIST_BUCKET * ctx->units * sizeof(vo_unit_result_dev);
     if (need <= ctx->dist_bytes) return VO_OK;
+    if (ctx->dist_head != ctx->dist_tail) { vo_set_error(ctx, "vo_dist_gather_post: the state grew while gathers are outstanding"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->dist_stream));
-    for (int k = 0; k < VO_DIST_DEPTH; k++) {
-        if (ctx->d_dist[k]) cudaFree(ctx->d_dist[k]);
-        if (ctx->h_dist[k]) cudaFreeHost(ctx->h_dist[k]);
-        VO_CUDA_CHECK(cudaMalloc(&ctx->d_dist[k], need));
-        VO_CUDA_CHECK(cudaMallocHost(&ctx->h_dist[k], need));
+    for (auto& bk : ctx->dist_bk) {
+        if (bk.d) cudaFree(bk.d);
+        if (bk.h) cudaFreeHost(bk.h);
+        bk.d = bk.h = nullptr;
+        VO_CUDA_CHECK(cudaMalloc(&bk.d, need));
+        VO_CUDA_CHECK(cudaMallocHost(&bk.h, need));
+        bk.fill = bk.unwaited = 0; bk.flushed = false;
     }
     ctx->dist_bytes = need;
     return VO_OK;
 }
 
-// all-gather of the result records of resident slots [first_unit, first_unit + n_units) (every rank posts the same n_units),
-// asynchronous on the communication stream; up to VO_DIST_DEPTH posts may be outstanding.  The records are copied to their
-// place in the ring entry's table first (device to device, this rank only) and gathered IN PLACE from there: the slots are
-// free again as soon as that local copy is done, so refilling them never waits for the slowest rank's contribution.
+// the exchange of one bucket: in-place all-gather of VO_DIST_BUCKET step snapshots per rank (a constant size, whatever
+// the fill, so every rank issues the same collective) + one copy of the whole table to pinned memory
+static int dist_flush(vo_ctx* ctx, int b)
+{
+    vo_ctx::DistBucket& bk = ctx->dist_bk[b];
+    const size_t per_rank = (size_t)VO_DIST_BUCKET * bk.n_units * sizeof(vo_unit_result_dev);
+    uint8_t* table = (uint8_t*)bk.d;
+    const int nrc = g_nccl.AllGather(table + (size_t)ctx->dist_rank * per_rank, table, per_rank, /*ncclUint8*/ 1, (NcclComm)ctx->dist_comm, ctx->dist_stream);
+    if (nrc != 0) { vo_set_error(ctx, "ncclAllGather: %s", nccl_err(nrc)); return VO_E_CUDA; }
+    VO_CUDA_CHECK(cudaMemcpyAsync(bk.h, table, per_rank * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->dist_stream));
+    VO_CUDA_CHECK(cudaEventRecord(bk.done, ctx->dist_stream));
+    bk.flushed = true;
+    if (b == ctx->dist_cur) ctx->dist_cur = (ctx->dist_cur + 1) % VO_DIST_NB;      // closed: later posts open the next bucket
+    return VO_OK;
+}
+
+// Posts the result records of resident slots [first_unit, first_unit + n_units) (every rank posts the same n_units) for the
+// gather; asynchronous, up to VO_DIST_DEPTH posts may be outstanding.  The post itself is a device-to-device snapshot into
+// the open bucket, so the slots may be refilled at once and no rank ever waits for another one here; the collective runs once
+// per VO_DIST_BUCKET posts (or when vo_dist_gather_wait needs a step of a bucket that has not been exchanged yet).
 extern "C" int vo_dist_gather_post(vo_ctx* ctx, int first_unit, int n_units)
 {
     if (!ctx) return VO_E_INVALID;
@@ -102,51 +126,59 @@ extern "C" int vo_dist_gather_post(vo_ctx* ctx, int first_unit, int n_units)
     if (first_unit < 0 || n_units <= 0 || first_unit + n_units > ctx->units) { vo_set_error(ctx, "vo_dist_gather_post: slots outside the state"); return VO_E_INVALID; }
     if (ctx->dist_head - ctx->dist_tail >= VO_DIST_DEPTH) { vo_set_error(ctx, "vo_dist_gather_post: %d gathers are already outstanding (vo_dist_gather_wait)", VO_DIST_DEPTH); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    int rc = dist_buffers(ctx, n_units);
+    int rc = dist_buffers(ctx);
     if (rc) return rc;
-    const int k = (int)(ctx->dist_head % VO_DIST_DEPTH);
+    if (ctx->dist_bk[ctx->dist_cur].fill > 0 && ctx->dist_bk[ctx->dist_cur].n_units != n_units && (rc = dist_flush(ctx, ctx->dist_cur))) return rc;
+    const int b = ctx->dist_cur;
+    vo_ctx::DistBucket& bk = ctx->dist_bk[b];
+    if (bk.fill == 0) {
+        if (bk.unwaited > 0) { vo_set_error(ctx, "vo_dist_gather_post: no free bucket (vo_dist_gather_wait)"); return VO_E_INVALID; }
+        bk.flushed = false; bk.n_units = n_units;
+    }
     // the records were written by work that the caller's stream has already been made to wait for (vo_batch_wait / vo_batch_run)
-    if (!ctx->dist_ev_fork) VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_fork, cudaEventDisableTiming));
     VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_fork, ctx->stream));
     VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->dist_stream, ctx->dist_ev_fork, 0));
     const size_t bytes = (size_t)n_units * sizeof(vo_unit_result_dev);
-    uint8_t* table = (uint8_t*)ctx->d_dist[k];
-    uint8_t* mine = table + (size_t)ctx->dist_rank * bytes;
-    VO_CUDA_CHECK(cudaMemcpyAsync(mine, ctx->d_results + first_unit, bytes, cudaMemcpyDeviceToDevice, ctx->dist_stream));
-    VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_read[k], ctx->dist_stream));          // the slot's records have been read
-    const int nrc = g_nccl.AllGather(mine, table, bytes, /*ncclUint8*/ 1, (NcclComm)ctx->dist_comm, ctx->dist_stream);
-    if (nrc != 0) { vo_set_error(ctx, "ncclAllGather: %s", nccl_err(nrc)); return VO_E_CUDA; }
-    VO_CUDA_CHECK(cudaMemcpyAsync(ctx->h_dist[k], table, bytes * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->dist_stream));
-    VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_done[k], ctx->dist_stream));
-    ctx->dist_posted[k] = true; ctx->dist_n[k] = n_units;
+    uint8_t* dst = (uint8_t*)bk.d + ((size_t)ctx->dist_rank * VO_DIST_BUCKET + bk.fill) * bytes;
+    VO_CUDA_CHECK(cudaMemcpyAsync(dst, ctx->d_results + first_unit, bytes, cudaMemcpyDeviceToDevice, ctx->dist_stream));
+    VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_read, ctx->dist_stream));             // the slots' records have been read
+    ctx->dist_steps[ctx->dist_head % (2 * VO_DIST_DEPTH)] = vo_ctx::DistStep{b, bk.fill};
+    bk.fill++; bk.unwaited++;
     ctx->dist_head++;
+    if (bk.fill == VO_DIST_BUCKET) return dist_flush(ctx, b);
     return VO_OK;
 }
 
-// the oldest outstanding gather: all[r * n_units + i] = record i of rank r's posted slots
+// the oldest outstanding post: all[r * n_units + i] = record i of rank r's posted slots
 extern "C" int vo_dist_gather_wait(vo_ctx* ctx, vo_unit_result* all, int cap_records, int* n_records)
 {
     if (!ctx) return VO_E_INVALID;
     if (ctx->dist_head == ctx->dist_tail) { vo_set_error(ctx, "vo_dist_gather_wait: nothing outstanding"); return VO_E_INVALID; }
-    const int k = (int)(ctx->dist_tail % VO_DIST_DEPTH);
+    const vo_ctx::DistStep st = ctx->dist_steps[ctx->dist_tail % (2 * VO_DIST_DEPTH)];
+    vo_ctx::DistBucket& bk = ctx->dist_bk[st.bucket];
+    const int n = ctx->dist_world * bk.n_units;
+    if (all && cap_records < n) { vo_set_error(ctx, "vo_dist_gather_wait: %d records, room for %d", n, cap_records); return VO_E_CAPACITY; }
     VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    VO_CUDA_CHECK(cudaEventSynchronize(ctx->dist_ev_done[k]));
-    const int n = ctx->dist_world * ctx->dist_n[k];
+    int rc;
+    if (!bk.flushed && (rc = dist_flush(ctx, st.bucket))) return rc;
+    VO_CUDA_CHECK(cudaEventSynchronize(bk.done));
     if (n_records) *n_records = n;
-    ctx->dist_tail++;
     if (all) {
-        if (cap_records < n) { vo_set_error(ctx, "vo_dist_gather_wait: %d records, room for %d", n, cap_records); return VO_E_CAPACITY; }
-        memcpy(all, ctx->h_dist[k], (size_t)n * sizeof(vo_unit_result));
+        const size_t bytes = (size_t)bk.n_units * sizeof(vo_unit_result);
+        for (int r = 0; r < ctx->dist_world; r++)
+            memcpy((uint8_t*)all + (size_t)r * bytes, (const uint8_t*)bk.h + ((size_t)r * VO_DIST_BUCKET + st.index) * bytes, bytes);
     }
+    ctx->dist_tail++;
+    if (--bk.unwaited == 0) bk.fill = 0;          // every step handed out: the bucket may be reused
     return VO_OK;
 }
 
-// a submission that refills resident slots must not overtake a gather that still reads their records
+// a submission that refills resident slots must not overtake the snapshot of a post that still reads their records
+// (the snapshots are ordered on the communication stream, so the latest one stands for all of them)
 int vo_dist_order_after_gathers(vo_ctx* ctx, cudaStream_t st)
 {
-    if (!ctx->dist_comm) return VO_OK;
-    for (int k = 0; k < VO_DIST_DEPTH; k++)
-        if (ctx->dist_posted[k]) VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->dist_ev_read[k], 0));
+    if (!ctx->dist_comm || ctx->dist_head == 0) return VO_OK;
+    VO_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->dist_ev_read, 0));
     return VO_OK;
 }
 
@@ -155,14 +187,15 @@ void vo_dist_shutdown(vo_ctx* ctx)
     if (ctx->dist_stream) cudaStreamSynchronize(ctx->dist_stream);
     if (ctx->dist_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((NcclComm)ctx->dist_comm);
     ctx->dist_comm = nullptr;
-    for (int k = 0; k < VO_DIST_DEPTH; k++) {
-        if (ctx->d_dist[k]) cudaFree(ctx->d_dist[k]);
-        if (ctx->h_dist[k]) cudaFreeHost(ctx->h_dist[k]);
-        if (ctx->dist_ev_read[k]) cudaEventDestroy(ctx->dist_ev_read[k]);
-        if (ctx->dist_ev_done[k]) cudaEventDestroy(ctx->dist_ev_done[k]);
-        ctx->d_dist[k] = nullptr; ctx->h_dist[k] = nullptr; ctx->dist_ev_read[k] = nullptr; ctx->dist_ev_done[k] = nullptr;
+    for (auto& bk : ctx->dist_bk) {
+        if (bk.d) cudaFree(bk.d);
+        if (bk.h) cudaFreeHost(bk.h);
+        if (bk.done) cudaEventDestroy(bk.done);
+        bk = vo_ctx::DistBucket();
     }
+    if (ctx->dist_ev_read) cudaEventDestroy(ctx->dist_ev_read);
     if (ctx->dist_ev_fork) cudaEventDestroy(ctx->dist_ev_fork);
     if (ctx->dist_stream) cudaStreamDestroy(ctx->dist_stream);
-    ctx->dist_ev_fork = nullptr; ctx->dist_stream = nullptr;
+    ctx->dist_ev_read = ctx->dist_ev_fork = nullptr; ctx->dist_stream = nullptr;
+    ctx->dist_head = ctx->dist_tail = 0; ctx->dist_cur = 0; ctx->dist_bytes = 0;
 }

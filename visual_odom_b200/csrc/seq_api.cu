@@ -153,7 +153,7 @@ static int seq_events(vo_ctx* ctx)
     }
     if (!ctx->side_stream[0]) {
         VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-        for (int c = 0; c < 2; c++) {
+        for (int c = 0; c < VO_LANES; c++) {
             VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side_stream[c], cudaStreamNonBlocking));
             VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->join_ev[c], cudaEventDisableTiming));
         }
