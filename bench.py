@@ -527,7 +527,7 @@ class Point:
             if s + D - 1 < n:
                 ctx.batch_submit(self.arr, ((s + D - 1) % D) * B, self.pitch)
             slot = (s % D) * B
-            out = ctx.batch_wait(slot, B)
+            out = ctx.batch_wait(slot, B, raw=True)            # the records as one structured array (no per-record Python objects)
             if self.full_outputs:                              # what matchingFeatures / trackingFrame2Frame hand back
                 self.last_outputs = [ctx.batch_outputs(slot + u, out[u], into=self.into[s % D][u]) for u in range(B)]
             if self.gather is not None:                        # result gather: fixed-size records over NCCL, non-blocking
@@ -536,7 +536,7 @@ class Point:
             self.tables = self.gather.drain()                  # the last tables arrive inside the timed region
         if ev:
             ev[1].record(self.stream)
-        return out
+        return ctx.records_to_dicts(out)
 
     def measure_e2e(self, steps, warmup, full_outputs=True, blocks=1):
         self.full_outputs = full_outputs
@@ -563,7 +563,7 @@ class NativeGather:
         self.ctx, self.B, self.outstanding, self.tables = ctx, B, 0, []
 
     def _harvest(self):
-        self.tables.append(self.ctx.dist_gather_wait(self.B))
+        self.tables.append(self.ctx.dist_gather_wait(self.B, raw=True))     # one array, not world x B dicts
         self.outstanding -= 1
 
     def post_step(self, slot, out, my_units):

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_path.py -x -q -m gpu -k "gather or pipelined" 2>&1 | tail -2
 run() { name=$1; n=$2; shift 2; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $n --steps 20 --warmup 3 --sweep 0 --cpu-seconds 0.3 > gpurun_out/diag_$name.json 2> gpurun_out/diag_$name.err
   python - "$name" <<'PY'
 import json,sys
@@ -10,6 +10,5 @@ try:
 except Exception as ex: print(n,'failed',ex); print(open(f'gpurun_out/diag_{n}.err').read()[-600:])
 PY
 }
-run bk_n2 2 A=1
-run bk_n2_nogather 2 VO_BENCH_GATHER=0
-run bk_n2_b 2 A=1
+run snap_n2 2 A=1
+run snap_n2_b 2 A=1

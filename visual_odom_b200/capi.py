@@ -46,6 +46,14 @@ class VoUnitResult(C.Structure):
     ]
 
 
+# the same record as a numpy structured dtype (C layout, 152 bytes): arrays of records can be handed out without building
+# one Python dict per record (a gathered table of a multi-GPU step has world x units of them)
+RESULT_DTYPE = np.dtype([("n_features", "<i4"), ("n_detected", "<i4"), ("n_tracked", "<i4"), ("n_valid", "<i4"), ("n_inliers", "<i4"),
+                         ("ransac_iters", "<i4"), ("pnp_status", "<i4"), ("rvec", "<f8", (3,)), ("tvec", "<f8", (3,)),
+                         ("R", "<f8", (3, 3))], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(VoUnitResult)
+
+
 # name -> (restype, argtypes); every symbol include/vo_b200.h declares must be listed here
 SIGNATURES = {
     "vo_default_params": (None, [C.POINTER(VoParams)]),
@@ -350,9 +358,13 @@ class Context:
         else:
             self._check(self.lib.vo_batch_submit(self.h, arr, first_unit, len(arr), pitch))
 
-    def batch_wait(self, first_unit, n_units):
+    def batch_wait(self, first_unit, n_units, raw=False):
+        """raw=True: the records as one numpy structured array (RESULT_DTYPE; fields are read as rec["n_valid"], rec["R"], ...)
+        instead of a list of dicts."""
         res = (VoUnitResult * n_units)()
         self._check(self.lib.vo_batch_wait(self.h, first_unit, n_units, res))
+        if raw:
+            return np.frombuffer(res, dtype=RESULT_DTYPE)
         return [self._result_dict(r) for r in res]
 
     @staticmethod
@@ -360,6 +372,12 @@ class Context:
         return dict(n_features=r.n_features, n_detected=r.n_detected, n_tracked=r.n_tracked, n_valid=r.n_valid,
                     n_inliers=r.n_inliers, ransac_iters=r.ransac_iters, pnp_status=r.pnp_status,
                     rvec=np.array(r.rvec[:]), tvec=np.array(r.tvec[:]), R=np.array(r.R[:]).reshape(3, 3))
+
+    @staticmethod
+    def records_to_dicts(arr):
+        """A RESULT_DTYPE array (batch_wait / dist_gather_wait with raw=True) as the list of dicts the other calls return."""
+        ints = ("n_features", "n_detected", "n_tracked", "n_valid", "n_inliers", "ransac_iters", "pnp_status")
+        return [dict({k: int(r[k]) for k in ints}, rvec=np.array(r["rvec"]), tvec=np.array(r["tvec"]), R=np.array(r["R"])) for r in arr]
 
     def batch_fetch(self, unit, res):
         nf, nv, ni = res["n_features"], res["n_valid"], res["n_inliers"]
@@ -400,10 +418,14 @@ class Context:
     def dist_gather_post(self, first_unit, n_units):
         self._check(self.lib.vo_dist_gather_post(self.h, int(first_unit), int(n_units)))
 
-    def dist_gather_wait(self, n_units):
+    def dist_gather_wait(self, n_units, raw=False):
+        """The oldest posted step's table (world x n_units records, rank-major).  raw=True: one numpy structured array
+        (RESULT_DTYPE) instead of world x n_units dicts."""
         res = (VoUnitResult * (self._dist_world * n_units))()
         n = C.c_int(0)
         self._check(self.lib.vo_dist_gather_wait(self.h, res, len(res), C.byref(n)))
+        if raw:
+            return np.frombuffer(res, dtype=RESULT_DTYPE)[:n.value]
         return [self._result_dict(r) for r in res[:n.value]]
 
     # ---- streaming sequence mode -------------------------------------------------------------------

@@ -100,7 +100,7 @@ struct vo_ctx {
     // multi-GPU record gather over NCCL (dist.cu); NCCL is dlopen'ed at vo_dist_init
     void* dist_comm = nullptr;
     int dist_rank = 0, dist_world = 1;
-    cudaStream_t dist_stream = nullptr;
+    cudaStream_t dist_stream = nullptr, dist_snap_stream = nullptr;     // collectives / per-post snapshots (never queued behind a collective)
     // up to VO_DIST_DEPTH posted steps outstanding.  A post only snapshots the records (device to device) into the open
     // bucket; a bucket is exchanged with ONE in-place all-gather + ONE copy to pinned memory when it holds VO_DIST_BUCKET
     // steps, or earlier when the host asks for one of its steps.

@@ -67,6 +67,7 @@ extern "C" int vo_dist_init(vo_ctx* ctx, const uint8_t id[128], int rank, int wo
     if (rc != 0) { vo_set_error(ctx, "ncclCommInitRank: %s", nccl_err(rc)); return VO_E_CUDA; }
     ctx->dist_comm = comm; ctx->dist_rank = rank; ctx->dist_world = world;
     VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->dist_stream, cudaStreamNonBlocking));
+    VO_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->dist_snap_stream, cudaStreamNonBlocking));
     VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_read, cudaEventDisableTiming));
     VO_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->dist_ev_fork, cudaEventDisableTiming));
     for (auto& bk : ctx->dist_bk) {
@@ -87,6 +88,7 @@ static int dist_buffers(vo_ctx* ctx)
     if (need <= ctx->dist_bytes) return VO_OK;
     if (ctx->dist_head != ctx->dist_tail) { vo_set_error(ctx, "vo_dist_gather_post: the state grew while gathers are outstanding"); return VO_E_INVALID; }
     VO_CUDA_CHECK(cudaStreamSynchronize(ctx->dist_stream));
+    VO_CUDA_CHECK(cudaStreamSynchronize(ctx->dist_snap_stream));
     for (auto& bk : ctx->dist_bk) {
         if (bk.d) cudaFree(bk.d);
         if (bk.h) cudaFreeHost(bk.h);
@@ -106,6 +108,7 @@ static int dist_flush(vo_ctx* ctx, int b)
     vo_ctx::DistBucket& bk = ctx->dist_bk[b];
     const size_t per_rank = (size_t)VO_DIST_BUCKET * bk.n_units * sizeof(vo_unit_result_dev);
     uint8_t* table = (uint8_t*)bk.d;
+    VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->dist_stream, ctx->dist_ev_read, 0));       // every snapshot of the bucket is in place
     const int nrc = g_nccl.AllGather(table + (size_t)ctx->dist_rank * per_rank, table, per_rank, /*ncclUint8*/ 1, (NcclComm)ctx->dist_comm, ctx->dist_stream);
     if (nrc != 0) { vo_set_error(ctx, "ncclAllGather: %s", nccl_err(nrc)); return VO_E_CUDA; }
     VO_CUDA_CHECK(cudaMemcpyAsync(bk.h, table, per_rank * ctx->dist_world, cudaMemcpyDeviceToHost, ctx->dist_stream));
@@ -136,12 +139,14 @@ extern "C" int vo_dist_gather_post(vo_ctx* ctx, int first_unit, int n_units)
         bk.flushed = false; bk.n_units = n_units;
     }
     // the records were written by work that the caller's stream has already been made to wait for (vo_batch_wait / vo_batch_run)
+    // The snapshot runs on its own stream: a collective that is waiting for a slower rank (or for an SM) on the
+    // communication stream must not hold back the snapshots behind it -- later submissions wait for those.
     VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_fork, ctx->stream));
-    VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->dist_stream, ctx->dist_ev_fork, 0));
+    VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->dist_snap_stream, ctx->dist_ev_fork, 0));
     const size_t bytes = (size_t)n_units * sizeof(vo_unit_result_dev);
     uint8_t* dst = (uint8_t*)bk.d + ((size_t)ctx->dist_rank * VO_DIST_BUCKET + bk.fill) * bytes;
-    VO_CUDA_CHECK(cudaMemcpyAsync(dst, ctx->d_results + first_unit, bytes, cudaMemcpyDeviceToDevice, ctx->dist_stream));
-    VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_read, ctx->dist_stream));             // the slots' records have been read
+    VO_CUDA_CHECK(cudaMemcpyAsync(dst, ctx->d_results + first_unit, bytes, cudaMemcpyDeviceToDevice, ctx->dist_snap_stream));
+    VO_CUDA_CHECK(cudaEventRecord(ctx->dist_ev_read, ctx->dist_snap_stream));        // the slots' records have been read
     ctx->dist_steps[ctx->dist_head % (2 * VO_DIST_DEPTH)] = vo_ctx::DistStep{b, bk.fill};
     bk.fill++; bk.unwaited++;
     ctx->dist_head++;
@@ -184,6 +189,7 @@ int vo_dist_order_after_gathers(vo_ctx* ctx, cudaStream_t st)
 
 void vo_dist_shutdown(vo_ctx* ctx)
 {
+    if (ctx->dist_snap_stream) cudaStreamSynchronize(ctx->dist_snap_stream);
     if (ctx->dist_stream) cudaStreamSynchronize(ctx->dist_stream);
     if (ctx->dist_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((NcclComm)ctx->dist_comm);
     ctx->dist_comm = nullptr;
@@ -196,6 +202,7 @@ void vo_dist_shutdown(vo_ctx* ctx)
     if (ctx->dist_ev_read) cudaEventDestroy(ctx->dist_ev_read);
     if (ctx->dist_ev_fork) cudaEventDestroy(ctx->dist_ev_fork);
     if (ctx->dist_stream) cudaStreamDestroy(ctx->dist_stream);
-    ctx->dist_ev_read = ctx->dist_ev_fork = nullptr; ctx->dist_stream = nullptr;
+    if (ctx->dist_snap_stream) cudaStreamDestroy(ctx->dist_snap_stream);
+    ctx->dist_ev_read = ctx->dist_ev_fork = nullptr; ctx->dist_stream = ctx->dist_snap_stream = nullptr;
     ctx->dist_head = ctx->dist_tail = 0; ctx->dist_cur = 0; ctx->dist_bytes = 0;
 }
