@@ -186,7 +186,10 @@ def test_record_gather_ring_world_of_one(built):
             c.dist_gather_post(0, B)
         assert len({tuple(r["tvec"]) for res in expect for r in res}) == VO_DIST_DEPTH * B      # the steps really differ
         for k in range(VO_DIST_DEPTH):
-            got = c.dist_gather_wait(B)
+            got = c.dist_gather_wait(B, raw=(k % 2 == 1))         # every other table as one structured array (RESULT_DTYPE)
+            if k % 2 == 1:
+                assert got.dtype.itemsize == 152 and got["n_valid"].shape == (B,)
+                got = c.records_to_dicts(got)
             assert len(got) == B
             for a, b in zip(got, expect[k]):
                 assert a["n_inliers"] == b["n_inliers"] and a["n_valid"] == b["n_valid"]
