@@ -65,3 +65,26 @@ def test_sass_has_tma_and_no_legacy_tensor_ops(built):
     sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTMALDG" in sass
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_result_record_numpy_view_matches_the_ctypes_struct():
+    """capi.RESULT_DTYPE (what batch_wait / dist_gather_wait hand out with raw=True) is the C record, field for field."""
+    import ctypes as C
+    import numpy as np
+    from visual_odom_b200 import capi
+    res = (capi.VoUnitResult * 3)()
+    for i, r in enumerate(res):
+        r.n_features, r.n_detected, r.n_tracked, r.n_valid, r.n_inliers, r.ransac_iters, r.pnp_status = [10 * i + k for k in range(7)]
+        for k in range(3):
+            r.rvec[k] = 0.5 * i + k; r.tvec[k] = -1.0 * i - k
+        for k in range(9):
+            r.R[k] = 100 * i + k
+    arr = np.frombuffer(res, dtype=capi.RESULT_DTYPE)
+    assert arr.dtype.itemsize == C.sizeof(capi.VoUnitResult) == 152
+    a = capi.Context.records_to_dicts(arr)
+    b = [capi.Context._result_dict(r) for r in res]
+    for x, y in zip(a, b):
+        assert set(x) == set(y)
+        for k in x:
+            assert np.array_equal(x[k], y[k]), k
+        assert x["R"].shape == (3, 3) and isinstance(x["n_valid"], int)
