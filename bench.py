@@ -7,12 +7,15 @@
 One "step" = one pass of the whole path (FAST -> select 2000 -> pyramids -> LK ring -> filters ->
 triangulation -> PnP/RANSAC) over `--units` independent KITTI-shaped synthetic stereo pairs per GPU.
 Prints ONE JSON line (see README "bench contract"):
-  value      frames/s, inputs resident in HBM when the timed region starts (vo_batch_run only)
-  e2e        frames/s through the C-ABI with pinned HOST buffers: H2D of the 4 images per unit +
-             run + D2H of the result records inside the timed region (vo_frame_batch)
+  value      frames/s, inputs resident in HBM when the timed region starts (vo_batch_submit(units = NULL) / vo_batch_wait,
+             two submissions in flight, L2 flushed before every submission)
+  e2e        frames/s through the C-ABI with pinned HOST buffers: H2D of the 4 images per unit + run + D2H of the result
+             records AND of every unit's point lists inside the timed region (vo_batch_submit / vo_batch_wait /
+             vo_batch_outputs, three submissions in flight; with N GPUs the record gather vo_dist_* is inside too)
   roofline   LK ring kernel: algorithmic bytes (17044 B per feature-ring) / its own
-             CUDA-event time on the launching stream, vs the measured HBM copy bandwidth
+             CUDA-event time on the launching stream, vs the measured HBM copy bandwidth; + the feature sweep
   cpu_baseline  cv2 (the OpenCV the reference links) through the reference glue, timed on this host
+  parity     one unit per rank checked against the cv2 oracle outside the timed region
 """
 import argparse
 import json
