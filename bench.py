@@ -807,6 +807,7 @@ def main():
                             "are inside the timed region" + ("; the NCCL all-gather of the records runs non-blocking on a side stream and "
                                                              "is drained inside the timed region (" + gather.kind + ")" if gather is not None else
                                                             ("; record gather DISABLED by VO_BENCH_GATHER=0 (diagnostic run)" if world > 1 else "")),
+                    "l2": "no flush on this path: every step's inputs are new bytes arriving over PCIe (the resident path flushes instead)",
                     "host_numa_binding": numa,
                     "summary_only": {"value": frames / (ms_sum * 1e-3), "d2h_bytes_per_step": d2h_records,
                                      "note": "round-1 definition: result records only"},

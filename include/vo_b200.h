@@ -187,7 +187,10 @@ VO_API int vo_frame_batch(vo_ctx* ctx, const vo_unit* units, int n_units, size_t
  * from units[0 .. n_units) (units == NULL: re-run what is resident there), runs the whole path on them and stages their
  * result records, all asynchronously; vo_batch_wait blocks until that submission is done and copies the records out.
  * Submissions on disjoint slot ranges overlap on the GPU (H2D and the latency-bound PnP tail of one under the LK ring of
- * the other), e.g. configure 2 x B units and keep two submissions of B in flight.  The host images of a submission
+ * the other).  The library runs up to three submissions concurrently (three lanes of streams): with inputs resident on
+ * the device two in flight saturate the GPU; with inputs coming from the host configure 3 x B units and keep three
+ * submissions of B in flight, so that the upload of step s+2 is already queued while the host reads step s (otherwise the
+ * host's enqueue time and the H2D copy sit between two steps of the GPU).  The host images of a submission
  * must stay valid (and, for a true async copy, be pinned) until it has been waited for; a slot range must be waited
  * for before it is submitted again.  vo_batch_fetch of a waited slot is valid until that slot is resubmitted. */
 VO_API int vo_batch_submit(vo_ctx* ctx, const vo_unit* units, int first_unit, int n_units, size_t pitch);
