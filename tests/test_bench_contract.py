@@ -40,3 +40,36 @@ def test_non_rank0_reference_arm_exits_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_native_gather_bookkeeping_never_exceeds_the_library_depth():
+    """bench.NativeGather (host side of the C-ABI record gather): posts every step, harvests the oldest table only when
+    VO_DIST_DEPTH posts are outstanding, drains in order -- checked against a stub context that enforces the library's rule."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from visual_odom_b200.capi import VO_DIST_DEPTH
+
+    class Stub:
+        def __init__(self):
+            self.posted, self.waited, self.max_out = 0, 0, 0
+
+        def dist_gather_post(self, slot, n):
+            assert self.posted - self.waited < VO_DIST_DEPTH, "the library would refuse this post"
+            self.posted += 1
+            self.max_out = max(self.max_out, self.posted - self.waited)
+
+        def dist_gather_wait(self, n, raw=False):
+            assert self.waited < self.posted and raw
+            self.waited += 1
+            return self.waited - 1
+
+    ctx = Stub()
+    g = bench.NativeGather(ctx, 8)
+    assert g.DEPTH == VO_DIST_DEPTH
+    for s in range(20):
+        g.post_step((s % 3) * 8, None, None)
+    tables = g.drain()
+    assert tables == list(range(20)) and ctx.posted == ctx.waited == 20 and ctx.max_out == VO_DIST_DEPTH
+    assert g.drain() == []
