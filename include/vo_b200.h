@@ -134,7 +134,7 @@ VO_API int vo_triangulate_homogeneous(vo_ctx* ctx, const float P_l[12], const fl
  *   inliers[n]   ascending inlier indices (CV_32S column in the reference), *n_inliers their count
  *   R_out        row-major 3x3 double = Rodrigues(rvec)
  * n == 4: as OpenCV, no RANSAC: the P3P pose of the first three points that reprojects the fourth best, unrefined, all
- * four reported as inliers, *ransac_iters = 0 (agrees with cv2 to <= 1e-5 on [R|t]; csrc/p3p_math.cuh).
+ * four reported as inliers, *ransac_iters = 0 (agrees with cv2 to <= 1e-6 on [R|t] in generic scenes; csrc/p3p_math.cuh).
  * Returns VO_E_TOO_FEW_POINTS for n < 4 (the reference would abort with cv::Exception). */
 VO_API int vo_pnp_ransac(vo_ctx* ctx, const vo_point3f* X, const vo_point2f* x, int n, const float K[9],
                          double rvec_io[3], double tvec_io[3], int32_t* inliers, int* n_inliers,

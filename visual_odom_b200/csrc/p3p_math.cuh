@@ -7,11 +7,13 @@
 // an operation-for-operation copy of OpenCV's solver: distances s1, s2 = u s1, s3 = v s1 along the unit bearings,
 //   u = N(v) / D(v),  N = (K - 1) v^2 - 2 K cos(beta) v + (K + 1),  D = 2 (cos(gamma) - v cos(alpha)),  K = (a^2 - c^2) / b^2
 //   quartic in v:  D^2 + N^2 - 2 cos(gamma) N D - (c^2 / b^2) (1 + v^2 - 2 v cos(beta)) D^2 = 0
-// built by polynomial products, all roots by poly_roots, then the rigid motion from the two triangles' orthonormal frames.
+// built by polynomial products, all roots by poly_roots (polished, near-double roots re-derived, see below), then the rigid
+// motion from the two triangles' orthonormal frames.
 // What IS reproduced from OpenCV: the image points are normalised as cv::undistortPoints does (f64 arithmetic, stored f32),
-// which is what bounds the agreement with cv2 (measured <= 1e-5 on [R|t] over 2000 random sets, tolerance asked 1e-4;
-// same solution picked every time).  Restated in oracle/pnp_ref.py (p3p_four_points) and pinned against cv2 there.
-// Where cv2's P3P returns NaN poses (seen on ~0.15 % of random sets) this returns "no model" instead.
+// and K is the float matrix the reference builds.  Agreement with cv2 (tests/test_oracle_pnp.py, this header compiled for
+// the host): a pose whenever cv2 has one, the same solution picked, [R|t] within 4e-7 on generic scenes, 4e-5 on
+// ill-conditioned 0.3 m point clusters (1e-4 asked).  Restated in oracle/pnp_ref.py (p3p_four_points).
+// Where cv2's P3P returns NaN poses (~0.3 % of random sets) this returns "no model" instead.
 #pragma once
 #include "ess_math.cuh"
 
@@ -66,33 +68,97 @@ VO_HDN inline int p3p_solutions(const double X[3][3], const double y[3][2], doub
     const int nr = poly_roots(poly, 4, roots);
     double Fw[9];
     if (!p3p_frame(X, Fw)) return 0;
+    // ---- real roots of the quartic ------------------------------------------------------------------------------------
+    // Two real roots that nearly coincide (poses next to Grunert's singularity, clustered points) come out of any root finder
+    // with errors ~ sqrt(eps), often as a conjugate pair with a small imaginary part: such a pair is re-derived from the local
+    // parabola around the extremum of the quartic, p(v) ~ A ((v - vm)^2 + s), real iff s <= 0.  Every root is polished by
+    // Newton steps on the real quartic (this alone takes the agreement with cv2 from 6e-5 to 1e-6 on generic scenes).
+    auto pval = [&](double v) { return (((poly[4] * v + poly[3]) * v + poly[2]) * v + poly[1]) * v + poly[0]; };
+    auto pd1 = [&](double v) { return ((4 * poly[4] * v + 3 * poly[3]) * v + 2 * poly[2]) * v + poly[1]; };
+    auto pd2 = [&](double v) { return (12 * poly[4] * v + 6 * poly[3]) * v + 2 * poly[2]; };
+    auto pabs = [&](double v) { v = fabs(v); return (((fabs(poly[4]) * v + fabs(poly[3])) * v + fabs(poly[2])) * v + fabs(poly[1])) * v + fabs(poly[0]); };
+    auto polish = [&](double v) {
+        for (int it = 0; it < 4; it++) {
+            const double dv = pd1(v);
+            if (dv == 0.0) break;
+            v -= pval(v) / dv;
+        }
+        return v;
+    };
+    double vs[8];
+    int nv = 0;
+    for (int i = 0; i < nr && nv < 7; i++) {
+        const double re = roots[i].re, im = roots[i].im;
+        const double mag = fabs(re) > 1.0 ? fabs(re) : 1.0;
+        if (fabs(im) <= 1e-9 * mag) {
+            vs[nv++] = polish(re);
+        } else if (im > 0 && im <= 1e-3 * mag) {
+            double vm = re;
+            for (int it = 0; it < 4; it++) {                  // extremum: Newton on p'
+                const double dd = pd2(vm);
+                if (dd == 0.0) break;
+                vm -= pd1(vm) / dd;
+            }
+            const double A = 0.5 * pd2(vm);
+            if (A != 0.0) {
+                const double sq = pval(vm) / A;
+                if (sq <= 0) {
+                    const double dl = sqrt(-sq);
+                    if (dl > 1e-12 * mag) { vs[nv++] = polish(vm - dl); vs[nv++] = polish(vm + dl); }
+                    else vs[nv++] = vm;
+                }
+            }
+        }
+    }
+    // ---- one pose per (v, u) ------------------------------------------------------------------------------------------
     int count = 0;
-    for (int i = 0; i < nr && count < 4; i++) {
-        const double v = roots[i].re;
-        const double mag = fabs(v) > 1.0 ? fabs(v) : 1.0;
-        if (fabs(roots[i].im) > 1e-9 * mag) continue;
-        if (!(v > 0)) continue;
-        const double Dv = D[0] + D[1] * v;
-        if (fabs(Dv) < 1e-12) continue;
-        const double u = (N[0] + N[1] * v + N[2] * v * v) / Dv;
-        if (!(u > 0)) continue;
+    double uv_seen[8];
+    for (int i = 0; i < nv && count < 4; i++) {
+        const double v = vs[i];
+        if (!(fabs(pval(v)) <= 1e-9 * pabs(v)) || !(v > 0)) continue;
         const double q = 1 + v * v - 2 * v * cb;
         if (!(q > 0)) continue;
-        const double s1 = sqrt(b2 / q);
-        const double s[3] = {s1, u * s1, v * s1};
-        double P[3][3], Fc[9];
-        for (int j = 0; j < 3; j++)
-            for (int k = 0; k < 3; k++) P[j][k] = f[j][k] * s[j];
-        if (!p3p_frame(P, Fc)) continue;
-        double* R = R_out + 9 * count;
-        double* t = t_out + 3 * count;
-        for (int r = 0; r < 3; r++)
-            for (int c = 0; c < 3; c++) R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
-        for (int r = 0; r < 3; r++) t[r] = P[0][r] - (R[r * 3 + 0] * X[0][0] + R[r * 3 + 1] * X[0][1] + R[r * 3 + 2] * X[0][2]);
-        bool finite = true;
-        for (int k = 0; k < 9; k++) finite &= (R[k] == R[k]) && fabs(R[k]) <= 2.0;
-        for (int k = 0; k < 3; k++) finite &= (t[k] == t[k]) && fabs(t[k]) < 1e300;
-        if (finite) count++;
+        // u = N(v) / D(v); next to the singularity D(v) -> 0 (N(v) -> 0 too) the quotient only selects which root of the
+        // quadratic u^2 - 2 cos(gamma) u + 1 - (c^2 / b^2) q = 0 (the third distance equation) belongs to this v
+        double us[2];
+        int nu = 0;
+        const double Dv = D[0] + D[1] * v;
+        const double rel = fabs(Dv) / (fabs(D[0]) + fabs(D[1] * v));
+        const double u_lin = Dv != 0.0 ? (N[0] + N[1] * v + N[2] * v * v) / Dv : 0.0;
+        if (rel > 1e-3) {
+            us[nu++] = u_lin;
+        } else {
+            const double disc = cg * cg - 1 + (c2 / b2) * q;
+            if (disc >= 0) {
+                const double sq = sqrt(disc), u0 = cg + sq, u1 = cg - sq;
+                if (rel > 1e-9) us[nu++] = fabs(u0 - u_lin) <= fabs(u1 - u_lin) ? u0 : u1;
+                else { us[nu++] = u0; us[nu++] = u1; }
+            }
+        }
+        for (int k = 0; k < nu && count < 4; k++) {
+            const double u = us[k];
+            if (!(u > 0)) continue;
+            // the other distance equation must hold as well (it does by construction on the linear branch)
+            if (fabs(u * u + v * v - 2 * u * v * ca - (a2 / b2) * q) > 1e-5 * (u * u + v * v + (a2 / b2) * q)) continue;
+            bool dup = false;
+            for (int j = 0; j < count; j++) dup = dup || (fabs(uv_seen[2 * j] - u) <= 1e-7 * u && fabs(uv_seen[2 * j + 1] - v) <= 1e-7 * v);
+            if (dup) continue;
+            const double s1 = sqrt(b2 / q);
+            const double s[3] = {s1, u * s1, v * s1};
+            double P[3][3], Fc[9];
+            for (int j = 0; j < 3; j++)
+                for (int kk = 0; kk < 3; kk++) P[j][kk] = f[j][kk] * s[j];
+            if (!p3p_frame(P, Fc)) continue;
+            double* R = R_out + 9 * count;
+            double* t = t_out + 3 * count;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) R[r * 3 + c] = Fc[r * 3 + 0] * Fw[c * 3 + 0] + Fc[r * 3 + 1] * Fw[c * 3 + 1] + Fc[r * 3 + 2] * Fw[c * 3 + 2];
+            for (int r = 0; r < 3; r++) t[r] = P[0][r] - (R[r * 3 + 0] * X[0][0] + R[r * 3 + 1] * X[0][1] + R[r * 3 + 2] * X[0][2]);
+            bool finite = true;
+            for (int kk = 0; kk < 9; kk++) finite &= (R[kk] == R[kk]) && fabs(R[kk]) <= 2.0;
+            for (int kk = 0; kk < 3; kk++) finite &= (t[kk] == t[kk]) && fabs(t[kk]) < 1e300;
+            if (finite) { uv_seen[2 * count] = u; uv_seen[2 * count + 1] = v; count++; }
+        }
     }
     return count;
 }
